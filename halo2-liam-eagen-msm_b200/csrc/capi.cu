@@ -1,0 +1,366 @@
+// extern "C" surface of libeagen_msm.so (declared in include/eagen_msm.h).  Plain pointers and sizes only.
+// There is no CPU fallback anywhere below: without a CUDA device eagen_ctx_create fails with EAGEN_E_NO_DEVICE.
+#include "engine.cuh"
+
+using namespace eagen;
+
+struct eagen_ctx {
+    int curve;
+    IEngine* eng;
+    std::string err;
+};
+struct eagen_result {
+    ResultImpl* r;
+};
+
+namespace {
+thread_local std::string g_global_err;
+
+template <class Fn>
+int guarded(eagen_ctx* ctx, Fn fn) {
+    try {
+        fn();
+        return EAGEN_OK;
+    } catch (const StatusError& e) {
+        if (ctx) ctx->err = e.msg; else g_global_err = e.msg;
+        return e.code;
+    } catch (const CudaError& e) {
+        if (ctx) ctx->err = e.msg; else g_global_err = e.msg;
+        cudaGetLastError();
+        return e.code;
+    } catch (const std::exception& e) {
+        if (ctx) ctx->err = e.what(); else g_global_err = e.what();
+        return EAGEN_E_ARG;
+    }
+}
+void need(bool ok, const char* what) { if (!ok) throw StatusError{EAGEN_E_ARG, what}; }
+
+template <class FS> uint32_t digits_for(uint8_t base) { return make_negbase_params<FS>(base).d; }
+uint32_t digits_of_curve(int curve, uint8_t base) {
+    switch (curve) {
+        case EAGEN_CURVE_PALLAS: return digits_for<Pallas::Scalar>(base);
+        case EAGEN_CURVE_VESTA: return digits_for<Vesta::Scalar>(base);
+        case EAGEN_CURVE_GRUMPKIN: return digits_for<Grumpkin::Scalar>(base);
+    }
+    throw StatusError{EAGEN_E_ARG, "unknown curve id"};
+}
+template <class FP> void precomp(int which, uint64_t e, uint64_t* out) {
+    Fe<FP> r;
+    if (which == 0) r = pow2k(Fe<FP>::root_of_unity(), (unsigned)std::min<uint64_t>(e, 300));
+    else if (which == 1) r = pow2k(Fe<FP>::root_of_unity_inv(), (unsigned)std::min<uint64_t>(e, 300));
+    else { r = Fe<FP>::one(); for (uint64_t i = 0; i < e; ++i) r = mul(r, Fe<FP>::two_inv()); }
+    std::memcpy(out, r.v, 32);
+}
+}  // namespace
+
+extern "C" {
+
+const char* eagen_status_string(int s) {
+    switch (s) {
+        case EAGEN_OK: return "ok";
+        case EAGEN_E_ARG: return "invalid argument";
+        case EAGEN_E_LEN: return "incompatible amount of coefficients";
+        case EAGEN_E_RANGE: return "scalar out of range";
+        case EAGEN_E_SUM_NONZERO: return "points do not sum to the identity";
+        case EAGEN_E_NTT_TOO_LARGE: return "transform larger than the field's two-adicity";
+        case EAGEN_E_CUDA: return "CUDA error";
+        case EAGEN_E_NCCL: return "NCCL error";
+        case EAGEN_E_DIGITS: return "negbase expansion longer than d digits";
+        case EAGEN_E_DOMAIN: return "point on the evaluation domain";
+        case EAGEN_E_NO_DEVICE: return "no CUDA device (no CPU fallback)";
+        case EAGEN_E_EMPTY: return "empty point list";
+    }
+    return "unknown status";
+}
+
+int eagen_ctx_create(int curve, int device, eagen_ctx** out) {
+    if (!out) return EAGEN_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); g_global_err = "no CUDA device visible"; return EAGEN_E_NO_DEVICE; }
+    if (device < 0 || device >= ndev) { g_global_err = "device index out of range"; return EAGEN_E_ARG; }
+    eagen_ctx* c = new eagen_ctx{curve, nullptr, ""};
+    int rc = guarded(nullptr, [&] {
+        switch (curve) {
+            case EAGEN_CURVE_PALLAS: c->eng = make_engine_pallas(device); break;
+            case EAGEN_CURVE_VESTA: c->eng = make_engine_vesta(device); break;
+            case EAGEN_CURVE_GRUMPKIN: c->eng = make_engine_grumpkin(device); break;
+            default: throw StatusError{EAGEN_E_ARG, "unknown curve id"};
+        }
+    });
+    if (rc != EAGEN_OK) { delete c; return rc; }
+    *out = c;
+    return EAGEN_OK;
+}
+
+void eagen_ctx_destroy(eagen_ctx* ctx) {
+    if (!ctx) return;
+    delete ctx->eng;
+    delete ctx;
+}
+
+const char* eagen_last_error(const eagen_ctx* ctx) { return ctx ? ctx->err.c_str() : g_global_err.c_str(); }
+uint64_t eagen_launch_count(const eagen_ctx* ctx) { return ctx ? ctx->eng->launches() : 0; }
+
+int eagen_num_digits(int curve, uint8_t base, uint32_t* d) {
+    return guarded(nullptr, [&] { need(d && base >= 2, "eagen_num_digits: null output or base < 2"); *d = digits_of_curve(curve, base); });
+}
+
+int eagen_fft_precomp(int curve, int which, uint64_t exp, uint64_t* out) {
+    return guarded(nullptr, [&] {
+        need(out && which >= 0 && which <= 2, "eagen_fft_precomp: bad arguments");
+        switch (curve) {
+            case EAGEN_CURVE_PALLAS: precomp<Pallas::Base>(which, exp, out); break;
+            case EAGEN_CURVE_VESTA: precomp<Vesta::Base>(which, exp, out); break;
+            case EAGEN_CURVE_GRUMPKIN: precomp<Grumpkin::Base>(which, exp, out); break;
+            default: throw StatusError{EAGEN_E_ARG, "unknown curve id"};
+        }
+    });
+}
+
+int eagen_negbase_decompose(eagen_ctx* ctx, const uint64_t* scalars, size_t n, uint8_t base, uint8_t* digits) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] { need(base >= 2 && (n == 0 || (scalars && digits)), "eagen_negbase_decompose: bad arguments"); ctx->eng->negbase_host(scalars, n, base, digits); });
+}
+
+int eagen_precompute_multiplicities(eagen_ctx* ctx, const uint64_t* pts, size_t n, uint8_t base, uint64_t* out) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] { need(base >= 2 && (n == 0 || (pts && out)), "eagen_precompute_multiplicities: bad arguments"); ctx->eng->multiples_host(pts, n, base, out); });
+}
+
+int eagen_lhs_witness(eagen_ctx* ctx, const uint64_t* scalars, const uint64_t* pts, size_t n, uint8_t base, uint32_t flags, eagen_result** out) {
+    if (!ctx || !out) return EAGEN_E_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        need(base >= 2 && (n == 0 || (scalars && pts)), "eagen_lhs_witness: bad arguments");
+        *out = new eagen_result{ctx->eng->lhs_host(scalars, pts, n, base, flags)};
+    });
+}
+
+int eagen_dev_lhs_witness(eagen_ctx* ctx, const void* d_scalars, const void* d_pts, size_t n, uint8_t base, uint32_t flags, eagen_result** out) {
+    if (!ctx || !out) return EAGEN_E_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        need(base >= 2 && (n == 0 || (d_scalars && d_pts)), "eagen_dev_lhs_witness: bad arguments");
+        *out = new eagen_result{ctx->eng->lhs_dev(d_scalars, d_pts, n, base, flags)};
+    });
+}
+
+int eagen_divisor_witness(eagen_ctx* ctx, const uint64_t* pts, size_t n, uint32_t flags, uint64_t* out_point, eagen_result** out) {
+    if (!ctx || !out) return EAGEN_E_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        need(n == 0 || pts, "eagen_divisor_witness: null points");
+        *out = new eagen_result{ctx->eng->divisor_host(pts, n, flags, out_point)};
+    });
+}
+
+int eagen_dev_shard_sums(eagen_ctx* ctx, const void* d_scalars, const void* d_pts, size_t n, uint8_t base, void* d_planes, void* d_table, void* d_partial_sums) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] {
+        need(base >= 2 && d_partial_sums && (n == 0 || (d_scalars && d_pts && d_planes && d_table)), "eagen_dev_shard_sums: bad arguments");
+        ctx->eng->shard_sums_dev(d_scalars, d_pts, n, base, d_planes, d_table, d_partial_sums);
+    });
+}
+int eagen_dev_carry_chain(eagen_ctx* ctx, const void* d_partial_sums, int nparts, uint8_t base, void* d_carries) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] {
+        need(base >= 2 && d_partial_sums && d_carries && nparts >= 1, "eagen_dev_carry_chain: bad arguments");
+        ctx->eng->carry_chain_dev(d_partial_sums, nparts, base, d_carries);
+    });
+}
+int eagen_dev_trees(eagen_ctx* ctx, const void* d_planes, const void* d_table, const void* d_carries, size_t n, uint8_t base,
+                    uint32_t pos_begin, uint32_t pos_end, uint32_t flags, eagen_result** out) {
+    if (!ctx || !out) return EAGEN_E_ARG;
+    *out = nullptr;
+    return guarded(ctx, [&] {
+        need(base >= 2 && d_carries && (n == 0 || (d_planes && d_table)), "eagen_dev_trees: bad arguments");
+        *out = new eagen_result{ctx->eng->trees_dev(d_planes, d_table, d_carries, n, base, pos_begin, pos_end, flags)};
+    });
+}
+
+int eagen_synth_inputs(eagen_ctx* ctx, uint64_t seed, size_t n, uint64_t* scalars, uint64_t* pts) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] { need(n == 0 || (scalars && pts), "eagen_synth_inputs: null buffer"); ctx->eng->synth_host(seed, n, scalars, pts); });
+}
+int eagen_dev_synth_inputs(eagen_ctx* ctx, uint64_t seed, size_t n, void* d_scalars, void* d_pts) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] { need(n == 0 || (d_scalars && d_pts), "eagen_dev_synth_inputs: null buffer"); ctx->eng->synth_dev(seed, n, d_scalars, d_pts); });
+}
+
+int eagen_poly_mul(eagen_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* b, size_t lb, uint64_t* out) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] { need((la == 0 || a) && (lb == 0 || b) && (la + lb <= 1 || out), "eagen_poly_mul: null buffer"); ctx->eng->poly_mul_host(a, la, b, lb, out); });
+}
+int eagen_ntt(eagen_ctx* ctx, uint64_t* data, uint32_t log_n, int inverse) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] { need(data != nullptr, "eagen_ntt: null buffer"); ctx->eng->ntt_host(data, log_n, inverse); });
+}
+int eagen_batch_invert(eagen_ctx* ctx, uint64_t* elems, size_t n) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] { need(n == 0 || elems, "eagen_batch_invert: null buffer"); ctx->eng->batch_invert_host(elems, n); });
+}
+int eagen_eval_function(eagen_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* b, size_t lb, const uint64_t* pts, size_t n, uint64_t* out) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] {
+        need((la == 0 || a) && (lb == 0 || b) && (n == 0 || (pts && out)), "eagen_eval_function: null buffer");
+        ctx->eng->eval_host(a, la, b, lb, pts, n, out);
+    });
+}
+
+// ---- result accessors ------------------------------------------------------------------------------------
+uint32_t eagen_result_num_digits(const eagen_result* r) { return r ? r->r->d : 0; }
+size_t eagen_result_num_functions(const eagen_result* r) { return r ? r->r->nf : 0; }
+size_t eagen_result_poly_len(const eagen_result* r, size_t k, int which) {
+    if (!r || k >= r->r->nf) return 0;
+    return (size_t)(which == EAGEN_POLY_A ? r->r->la[k] : r->r->lb[k]);
+}
+int eagen_result_poly_copy(eagen_result* r, size_t k, int which, uint64_t* out) {
+    if (!r || k >= r->r->nf || (which != EAGEN_POLY_A && which != EAGEN_POLY_B)) return EAGEN_E_ARG;
+    ResultImpl* x = r->r;
+    size_t len = (size_t)(which == EAGEN_POLY_A ? x->la[k] : x->lb[k]);
+    if (len == 0) return EAGEN_OK;
+    if (!out) return EAGEN_E_ARG;
+    cudaSetDevice(x->device);
+    const char* src = (const char*)(which == EAGEN_POLY_A ? x->A.p : x->B.p) + k * (which == EAGEN_POLY_A ? x->a_stride : x->b_stride) * 32;
+    return cudaMemcpy(out, src, len * 32, cudaMemcpyDeviceToHost) == cudaSuccess ? EAGEN_OK : EAGEN_E_CUDA;
+}
+size_t eagen_result_total_bytes(const eagen_result* r) {
+    if (!r) return 0;
+    size_t t = 0;
+    for (size_t k = 0; k < r->r->nf; ++k) t += ((size_t)r->r->la[k] + (size_t)r->r->lb[k]) * 32;
+    return t;
+}
+int eagen_result_copy_all(eagen_result* r, uint64_t* out, size_t out_bytes, size_t* written) {
+    if (!r || !out) return EAGEN_E_ARG;
+    ResultImpl* x = r->r;
+    if (out_bytes < eagen_result_total_bytes(r)) return EAGEN_E_LEN;
+    cudaSetDevice(x->device);
+    char* dst = (char*)out;
+    for (size_t k = 0; k < x->nf; ++k) {
+        size_t la = (size_t)x->la[k] * 32, lb = (size_t)x->lb[k] * 32;
+        if (la && cudaMemcpyAsync(dst, (const char*)x->A.p + k * x->a_stride * 32, la, cudaMemcpyDeviceToHost, 0) != cudaSuccess) return EAGEN_E_CUDA;
+        dst += la;
+        if (lb && cudaMemcpyAsync(dst, (const char*)x->B.p + k * x->b_stride * 32, lb, cudaMemcpyDeviceToHost, 0) != cudaSuccess) return EAGEN_E_CUDA;
+        dst += lb;
+    }
+    if (cudaStreamSynchronize(0) != cudaSuccess) return EAGEN_E_CUDA;
+    if (written) *written = (size_t)(dst - (char*)out);
+    return EAGEN_OK;
+}
+int eagen_result_carry(eagen_result* r, uint64_t* out) {
+    if (!r || !out) return EAGEN_E_ARG;
+    std::memcpy(out, r->r->carry, 64);
+    return EAGEN_OK;
+}
+int eagen_result_carries(eagen_result* r, uint64_t* out) {
+    if (!r || !out) return EAGEN_E_ARG;
+    std::memcpy(out, r->r->carries.data(), r->r->carries.size() * 8);
+    return EAGEN_OK;
+}
+int eagen_result_digits(eagen_result* r, uint8_t* out) {
+    if (!r || !out || !r->r->has_digits) return EAGEN_E_ARG;
+    cudaSetDevice(r->r->device);
+    size_t bytes = r->r->n * r->r->d;
+    if (bytes == 0) return EAGEN_OK;
+    return cudaMemcpy(out, r->r->digits.p, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? EAGEN_OK : EAGEN_E_CUDA;
+}
+double eagen_result_device_ms(const eagen_result* r) { return r ? r->r->device_ms : 0.0; }
+int eagen_result_device_view(eagen_result* r, const void** d_a, size_t* a_stride, const void** d_b, size_t* b_stride) {
+    if (!r) return EAGEN_E_ARG;
+    if (d_a) *d_a = r->r->A.p;
+    if (a_stride) *a_stride = r->r->a_stride;
+    if (d_b) *d_b = r->r->B.p;
+    if (b_stride) *b_stride = r->r->b_stride;
+    return EAGEN_OK;
+}
+void eagen_result_free(eagen_result* r) {
+    if (!r) return;
+    cudaSetDevice(r->r->device);
+    delete r->r;
+    delete r;
+}
+
+}  // extern "C"
+
+// ---- host-side self-test hooks (include/eagen_msm_selftest.h): the HD arithmetic run on the CPU ------------
+#include "../../include/eagen_msm_selftest.h"
+namespace {
+template <class FP> void st_field(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    Fe<FP> x, y = Fe<FP>::zero(), r;
+    std::memcpy(x.v, a, 32);
+    if (b) std::memcpy(y.v, b, 32);
+    switch (op) {
+        case 0: r = add(x, y); break;
+        case 1: r = sub(x, y); break;
+        case 2: r = mul(x, y); break;
+        case 3: r = inv(x); break;
+        case 4: r = from_canonical(x); break;
+        case 5: r = to_canonical(x); break;
+        default: throw StatusError{EAGEN_E_ARG, "bad op"};
+    }
+    std::memcpy(out, r.v, 32);
+}
+template <class CC> void st_curve(int op, const uint64_t* p, const uint64_t* q, uint32_t k, uint64_t* out) {
+    typedef typename CC::Base F;
+    auto load = [](const uint64_t* s) { Fe<F> x, y, z; std::memcpy(x.v, s, 32); std::memcpy(y.v, s + 4, 32); std::memcpy(z.v, s + 8, 32); return jacobian_to_proj<CC>(x, y, z); };
+    Proj<F> a = load(p), r;
+    switch (op) {
+        case 0: r = padd<CC>(a, load(q)); break;
+        case 1: r = pdbl<CC>(a); break;
+        case 2: { Affine<F> qa; std::memcpy(qa.x.v, q, 32); std::memcpy(qa.y.v, q + 4, 32); r = padd_mixed<CC>(a, qa); break; }
+        case 3: r = pmul_small<CC>(a, k); break;
+        default: throw StatusError{EAGEN_E_ARG, "bad op"};
+    }
+    Affine<F> o = proj_to_affine(r, inv(r.z));
+    std::memcpy(out, &o, 64);
+}
+template <class FS> void st_nb(uint8_t base, uint32_t* d, uint32_t* chunk, uint32_t* cd, uint32_t* limbs) {
+    NegbaseParams p = make_negbase_params<FS>(base);
+    *d = p.d; *chunk = p.chunk; *cd = p.chunk_digits;
+    std::memcpy(limbs, p.sq, 32); std::memcpy(limbs + 8, p.K, 32); std::memcpy(limbs + 16, p.bd, 32);
+}
+}  // namespace
+
+extern "C" {
+int eagen_selftest_field(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    return guarded(nullptr, [&] {
+        need(a && out, "null");
+        switch (field) {
+            case 0: st_field<PallasFp>(op, a, b, out); break;
+            case 1: st_field<PallasFq>(op, a, b, out); break;
+            case 2: st_field<Bn256Fr>(op, a, b, out); break;
+            case 3: st_field<Bn256Fq>(op, a, b, out); break;
+            default: throw StatusError{EAGEN_E_ARG, "unknown field id"};
+        }
+    });
+}
+int eagen_selftest_curve(int curve, int op, const uint64_t* p, const uint64_t* q, uint32_t k, uint64_t* out) {
+    return guarded(nullptr, [&] {
+        need(p && out, "null");
+        switch (curve) {
+            case EAGEN_CURVE_PALLAS: st_curve<Pallas>(op, p, q, k, out); break;
+            case EAGEN_CURVE_VESTA: st_curve<Vesta>(op, p, q, k, out); break;
+            case EAGEN_CURVE_GRUMPKIN: st_curve<Grumpkin>(op, p, q, k, out); break;
+            default: throw StatusError{EAGEN_E_ARG, "unknown curve id"};
+        }
+    });
+}
+int eagen_selftest_negbase_params(int curve, uint8_t base, uint32_t* d, uint32_t* chunk, uint32_t* cd, uint32_t* limbs) {
+    return guarded(nullptr, [&] {
+        need(d && chunk && cd && limbs && base >= 2, "bad arguments");
+        switch (curve) {
+            case EAGEN_CURVE_PALLAS: st_nb<Pallas::Scalar>(base, d, chunk, cd, limbs); break;
+            case EAGEN_CURVE_VESTA: st_nb<Vesta::Scalar>(base, d, chunk, cd, limbs); break;
+            case EAGEN_CURVE_GRUMPKIN: st_nb<Grumpkin::Scalar>(base, d, chunk, cd, limbs); break;
+            default: throw StatusError{EAGEN_E_ARG, "unknown curve id"};
+        }
+    });
+}
+int eagen_selftest_ntt_plan(int t, int* pairs) {
+    if (!pairs || t < 1 || t > 40) return EAGEN_E_ARG;
+    auto v = ntt_plan(t);
+    for (size_t i = 0; i < v.size() && i < 8; ++i) { pairs[2 * i] = v[i].first; pairs[2 * i + 1] = v[i].second; }
+    return (int)v.size();
+}
+}

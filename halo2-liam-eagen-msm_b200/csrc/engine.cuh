@@ -1,0 +1,750 @@
+// Host-side orchestration of the witness path on one B200: memory plan, launch order, error mapping.
+// Templated on the curve; instantiated once per curve in engine_<curve>.cu, used through IEngine by capi.cu.
+//
+// Data flow (all device resident, one stream):
+//   scalars --K1--> digit planes (d x n)                                        HBM bound
+//   points  --K2--> multiples table (n x (b-1) affine)      one batched inversion
+//   planes+table --K3--> d partial sums --K4--> d carries (affine)
+//   planes+table+carries --scatter--> T_i for a group of digit positions (tmp of the reference)
+//   T_i --K5--> leaves --[K5 pair sums, K6 NTT, K7 merge, K9 inversions] x levels--> root (a, b) --K10--> canonical
+#pragma once
+#include <algorithm>
+#include <memory>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/eagen_msm.h"
+#include "kernels.cuh"
+
+namespace eagen {
+
+struct CudaError {
+    std::string msg;
+    int code;
+};
+
+#define EAGEN_CUDA(call)                                                                                        \
+    do {                                                                                                        \
+        cudaError_t e_ = (call);                                                                                \
+        if (e_ != cudaSuccess)                                                                                  \
+            throw CudaError{std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")", EAGEN_E_CUDA}; \
+    } while (0)
+
+struct StatusError {
+    int code;
+    std::string msg;
+};
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void* ensure(size_t bytes) {
+        if (bytes > cap) {
+            if (p) cudaFree(p);
+            p = nullptr; cap = 0;
+            size_t want = bytes + (bytes >> 3) + 256;
+            cudaError_t e = cudaMalloc(&p, want);
+            if (e != cudaSuccess) { p = nullptr; throw CudaError{std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e), EAGEN_E_CUDA}; }
+            cap = want;
+        }
+        return p;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    ~DevBuf() { release(); }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// ---- result handle -------------------------------------------------------------------------------------
+struct ResultImpl {
+    int device = 0;
+    uint32_t d = 0;
+    size_t n = 0;
+    size_t nf = 0;                       // functions held
+    size_t a_stride = 0, b_stride = 0;   // elements
+    DevBuf A, B;                         // nf x stride field elements
+    std::vector<int> la, lb;             // trimmed lengths
+    DevBuf digits;                       // n x d (optional)
+    bool has_digits = false;
+    std::vector<uint64_t> carries;       // d x 8 (host copy, tiny)
+    uint64_t carry[8] = {0};
+    double device_ms = 0;
+};
+
+struct IEngine {
+    virtual ~IEngine() {}
+    virtual int device() const = 0;
+    virtual uint64_t launches() const = 0;
+    virtual void negbase_host(const uint64_t* scalars, size_t n, uint8_t base, uint8_t* digits) = 0;
+    virtual void multiples_host(const uint64_t* pts, size_t n, uint8_t base, uint64_t* out) = 0;
+    virtual ResultImpl* lhs_host(const uint64_t* scalars, const uint64_t* pts, size_t n, uint8_t base, uint32_t flags) = 0;
+    virtual ResultImpl* lhs_dev(const void* d_scalars, const void* d_pts, size_t n, uint8_t base, uint32_t flags) = 0;
+    virtual ResultImpl* divisor_host(const uint64_t* pts, size_t n, uint32_t flags, uint64_t* out_point) = 0;
+    virtual void poly_mul_host(const uint64_t* a, size_t la, const uint64_t* b, size_t lb, uint64_t* out) = 0;
+    virtual void ntt_host(uint64_t* data, uint32_t log_n, int inverse) = 0;
+    virtual void batch_invert_host(uint64_t* elems, size_t n) = 0;
+    virtual void eval_host(const uint64_t* a, size_t la, const uint64_t* b, size_t lb, const uint64_t* pts, size_t n, uint64_t* out) = 0;
+    virtual void shard_sums_dev(const void* d_scalars, const void* d_pts, size_t n, uint8_t base, void* d_planes, void* d_table, void* d_sums) = 0;
+    virtual void carry_chain_dev(const void* d_sums, int nparts, uint8_t base, void* d_carries) = 0;
+    virtual void synth_dev(uint64_t seed, size_t n, void* d_scalars, void* d_pts) = 0;
+    virtual void synth_host(uint64_t seed, size_t n, uint64_t* scalars, uint64_t* pts) = 0;
+    virtual ResultImpl* trees_dev(const void* d_planes, const void* d_table, const void* d_carries, size_t n, uint8_t base,
+                                  uint32_t pos_begin, uint32_t pos_end, uint32_t flags) = 0;
+};
+
+// ---- small host big-integer helpers (order / isqrt / logb_ceil of the reference, host side) ---------------
+struct HostU256 {
+    uint32_t w[8];
+    static HostU256 zero() { HostU256 r; std::memset(r.w, 0, 32); return r; }
+    bool is_zero() const { for (int i = 0; i < 8; ++i) if (w[i]) return false; return true; }
+    uint32_t divmod_small(uint32_t dv) {
+        uint64_t rem = 0;
+        for (int i = 7; i >= 0; --i) { uint64_t cur = (rem << 32) | w[i]; w[i] = (uint32_t)(cur / dv); rem = cur % dv; }
+        return (uint32_t)rem;
+    }
+    bool mul_small_add(uint32_t m, uint32_t addv) {  // this = this*m + addv ; false on overflow
+        uint64_t c = addv;
+        for (int i = 0; i < 8; ++i) { c += (uint64_t)w[i] * m; w[i] = (uint32_t)c; c >>= 32; }
+        return c == 0;
+    }
+    int cmp(const HostU256& o) const {
+        for (int i = 7; i >= 0; --i) if (w[i] != o.w[i]) return w[i] < o.w[i] ? -1 : 1;
+        return 0;
+    }
+};
+
+// floor(sqrt(p)), bit-by-bit on a 128-bit candidate
+inline HostU256 host_isqrt(const HostU256& p) {
+    HostU256 r = HostU256::zero();
+    for (int bit = 127; bit >= 0; --bit) {
+        HostU256 c = r;
+        c.w[bit / 32] |= 1u << (bit % 32);
+        uint32_t sq[9] = {0};  // c is 4 limbs -> c^2 is 8 limbs
+        for (int i = 0; i < 4; ++i) {
+            uint64_t carry = 0;
+            for (int j = 0; j < 4; ++j) { carry += (uint64_t)c.w[i] * c.w[j] + sq[i + j]; sq[i + j] = (uint32_t)carry; carry >>= 32; }
+            sq[i + 4] += (uint32_t)carry;
+        }
+        HostU256 s; std::memcpy(s.w, sq, 32);
+        if (s.cmp(p) <= 0) r = c;
+    }
+    return r;
+}
+
+template <class FS>
+inline HostU256 host_order() { HostU256 r; for (int i = 0; i < 8; ++i) r.w[i] = FS::mod(i); return r; }
+
+// d and the K1 constants for (scalar field, base)      reference: src/argument_witness_calc.rs:89-91
+template <class FS>
+inline NegbaseParams make_negbase_params(uint8_t base) {
+    NegbaseParams p;
+    HostU256 sq = host_isqrt(host_order<FS>());
+    sq.mul_small_add(1, 2);
+    std::memcpy(p.sq, sq.w, 32);
+    uint32_t d = 0;
+    for (HostU256 x = sq; !x.is_zero(); x.divmod_small(base)) ++d;
+    p.d = d + 1;
+    p.base = base;
+    HostU256 K = HostU256::zero(), pw = HostU256::zero();
+    pw.w[0] = 1;  // base^i
+    for (uint32_t i = 0; i < p.d; ++i) {
+        if (i & 1) {  // K += (base-1) * base^i
+            uint64_t c = 0;
+            for (int l = 0; l < 8; ++l) { c += (uint64_t)pw.w[l] * (base - 1) + K.w[l]; K.w[l] = (uint32_t)c; c >>= 32; }
+        }
+        pw.mul_small_add(base, 0);
+    }
+    std::memcpy(p.K, K.w, 32);
+    std::memcpy(p.bd, pw.w, 32);
+    p.chunk_digits = 0; p.chunk = 1;
+    while ((uint64_t)p.chunk * base < (1ull << 32)) { p.chunk *= base; ++p.chunk_digits; }
+    return p;
+}
+
+inline int ceil_log2(size_t x) { int l = 0; while (((size_t)1 << l) < x) ++l; return l; }
+
+// forward order (descending stages) of shared-memory passes for a 2^t transform
+inline std::vector<std::pair<int, int>> ntt_plan(int t) {
+    std::vector<std::pair<int, int>> v;
+    if (t <= NTT_TILE_LOG) { v.push_back({t - 1, 0}); return v; }
+    int r = t - NTT_TILE_LOG, np = (r + 7) / 8, each = r / np, extra = r % np, s = t - 1;
+    for (int p = 0; p < np; ++p) { int k = each + (p < extra ? 1 : 0); v.push_back({s, s - k + 1}); s -= k; }
+    v.push_back({NTT_TILE_LOG - 1, 0});
+    return v;
+}
+
+template <class CC>
+class Engine : public IEngine {
+public:
+    typedef typename CC::Base FB;
+    typedef typename CC::Scalar FS;
+    typedef Fe<FB> F;
+    typedef Affine<FB> Aff;
+    typedef Proj<FB> Prj;
+
+    explicit Engine(int dev) : dev_(dev) {
+        EAGEN_CUDA(cudaSetDevice(dev_));
+        EAGEN_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+        EAGEN_CUDA(cudaMalloc(&d_err_, sizeof(int)));
+        EAGEN_CUDA(cudaMemsetAsync(d_err_, 0, sizeof(int), st_));
+        EAGEN_CUDA(cudaEventCreate(&ev0_));
+        EAGEN_CUDA(cudaEventCreate(&ev1_));
+        int one = 1;
+        EAGEN_CUDA(cudaMalloc(&d_one_, sizeof(int)));
+        EAGEN_CUDA(cudaMemcpyAsync(d_one_, &one, sizeof(int), cudaMemcpyHostToDevice, st_));
+        EAGEN_CUDA(cudaStreamSynchronize(st_));
+    }
+    ~Engine() override {
+        cudaSetDevice(dev_);
+        cudaStreamSynchronize(st_);
+        cudaFree(d_err_); cudaFree(d_one_);
+        cudaEventDestroy(ev0_); cudaEventDestroy(ev1_);
+        cudaStreamDestroy(st_);
+    }
+    int device() const override { return dev_; }
+    uint64_t launches() const override { return launches_; }
+
+    // ------------------------------------------------------------------------------------------------
+    // public operations
+    // ------------------------------------------------------------------------------------------------
+    void negbase_host(const uint64_t* scalars, size_t n, uint8_t base, uint8_t* digits) override {
+        use();
+        NegbaseParams prm = make_negbase_params<FS>(base);
+        if (n == 0) return;
+        Fe<FS>* ds = (Fe<FS>*)in_scalars_.ensure(n * 32);
+        uint8_t* planes = (uint8_t*)planes_.ensure(n * prm.d);
+        uint8_t* rows = (uint8_t*)rows_.ensure(n * prm.d);
+        EAGEN_CUDA(cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, st_));
+        run_negbase(ds, n, prm, planes, rows);
+        EAGEN_CUDA(cudaMemcpyAsync(digits, rows, n * prm.d, cudaMemcpyDeviceToHost, st_));
+        sync_check();
+    }
+
+    void multiples_host(const uint64_t* pts, size_t n, uint8_t base, uint64_t* out) override {
+        use();
+        if (n == 0) return;
+        F* dp = (F*)in_points_.ensure(n * 96);
+        Aff* tab = (Aff*)table_.ensure(n * (size_t)(base - 1) * 64);
+        EAGEN_CUDA(cudaMemcpyAsync(dp, pts, n * 96, cudaMemcpyHostToDevice, st_));
+        run_multiples(dp, n, base, tab);
+        EAGEN_CUDA(cudaMemcpyAsync(out, tab, n * (size_t)(base - 1) * 64, cudaMemcpyDeviceToHost, st_));
+        sync_check();
+    }
+
+    ResultImpl* lhs_host(const uint64_t* scalars, const uint64_t* pts, size_t n, uint8_t base, uint32_t flags) override {
+        use();
+        Fe<FS>* ds = (Fe<FS>*)in_scalars_.ensure(std::max<size_t>(n, 1) * 32);
+        F* dp = (F*)in_points_.ensure(std::max<size_t>(n, 1) * 96);
+        if (n) {
+            EAGEN_CUDA(cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, st_));
+            EAGEN_CUDA(cudaMemcpyAsync(dp, pts, n * 96, cudaMemcpyHostToDevice, st_));
+        }
+        return lhs_dev(ds, dp, n, base, flags);
+    }
+
+    ResultImpl* lhs_dev(const void* d_scalars, const void* d_pts, size_t n, uint8_t base, uint32_t flags) override {
+        use();
+        NegbaseParams prm = make_negbase_params<FS>(base);
+        const uint32_t d = prm.d;
+        EAGEN_CUDA(cudaEventRecord(ev0_, st_));
+        size_t nn = std::max<size_t>(n, 1);
+        uint8_t* planes = (uint8_t*)planes_.ensure(nn * d);
+        Aff* tab = (Aff*)table_.ensure(nn * (size_t)(base - 1) * 64);
+        Prj* sums = (Prj*)sums_.ensure((size_t)d * sizeof(Prj));
+        Aff* carries = (Aff*)carries_.ensure((size_t)d * sizeof(Aff));
+        uint8_t* rows = nullptr;
+        std::unique_ptr<ResultImpl> res(new ResultImpl());
+        res->device = dev_; res->d = d; res->n = n;
+        if (flags & EAGEN_KEEP_DIGITS) { rows = (uint8_t*)res->digits.ensure(nn * d); res->has_digits = true; }
+        run_shard_sums((const Fe<FS>*)d_scalars, (const F*)d_pts, n, prm, planes, rows, tab, sums);
+        run_carry_chain(sums, 1, d, base, carries);
+        res->carries.assign((size_t)d * 8, 0);
+        EAGEN_CUDA(cudaMemcpyAsync(res->carries.data(), carries, (size_t)d * 64, cudaMemcpyDeviceToHost, st_));
+        if (!(flags & EAGEN_NO_FUNCTIONS)) run_position_trees(planes, tab, carries, n, base, d, 0, d, flags, res.get());
+        EAGEN_CUDA(cudaEventRecord(ev1_, st_));
+        sync_check();
+        std::memcpy(res->carry, &res->carries[(size_t)(d - 1) * 8], 64);
+        float ms = 0; EAGEN_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+        res->device_ms = ms;
+        return res.release();
+    }
+
+    void shard_sums_dev(const void* d_scalars, const void* d_pts, size_t n, uint8_t base, void* d_planes, void* d_table, void* d_sums) override {
+        use();
+        NegbaseParams prm = make_negbase_params<FS>(base);
+        run_shard_sums((const Fe<FS>*)d_scalars, (const F*)d_pts, n, prm, (uint8_t*)d_planes, nullptr, (Aff*)d_table, (Prj*)d_sums);
+        sync_check();
+    }
+    void carry_chain_dev(const void* d_sums, int nparts, uint8_t base, void* d_carries) override {
+        use();
+        NegbaseParams prm = make_negbase_params<FS>(base);
+        run_carry_chain((const Prj*)d_sums, nparts, prm.d, base, (Aff*)d_carries);
+        sync_check();
+    }
+    ResultImpl* trees_dev(const void* d_planes, const void* d_table, const void* d_carries, size_t n, uint8_t base,
+                          uint32_t pos_begin, uint32_t pos_end, uint32_t flags) override {
+        use();
+        NegbaseParams prm = make_negbase_params<FS>(base);
+        if (pos_begin > pos_end || pos_end > prm.d) throw StatusError{EAGEN_E_ARG, "digit position range out of bounds"};
+        std::unique_ptr<ResultImpl> res(new ResultImpl());
+        res->device = dev_; res->d = prm.d; res->n = n;
+        EAGEN_CUDA(cudaEventRecord(ev0_, st_));
+        res->carries.assign((size_t)prm.d * 8, 0);
+        EAGEN_CUDA(cudaMemcpyAsync(res->carries.data(), d_carries, (size_t)prm.d * 64, cudaMemcpyDeviceToHost, st_));
+        run_position_trees((const uint8_t*)d_planes, (const Aff*)d_table, (const Aff*)d_carries, n, base, prm.d, pos_begin, pos_end, flags, res.get());
+        EAGEN_CUDA(cudaEventRecord(ev1_, st_));
+        sync_check();
+        std::memcpy(res->carry, &res->carries[(size_t)(prm.d - 1) * 8], 64);
+        float ms = 0; EAGEN_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+        res->device_ms = ms;
+        return res.release();
+    }
+
+    void synth_dev(uint64_t seed, size_t n, void* d_scalars, void* d_pts) override {
+        use();
+        launch(k_synth_inputs<CC>, n, 128, seed, n, (Fe<FS>*)d_scalars, (F*)d_pts);
+        sync_check();
+    }
+    void synth_host(uint64_t seed, size_t n, uint64_t* scalars, uint64_t* pts) override {
+        use();
+        if (!n) return;
+        Fe<FS>* ds = (Fe<FS>*)in_scalars_.ensure(n * 32);
+        F* dp = (F*)in_points_.ensure(n * 96);
+        launch(k_synth_inputs<CC>, n, 128, seed, n, ds, dp);
+        EAGEN_CUDA(cudaMemcpyAsync(scalars, ds, n * 32, cudaMemcpyDeviceToHost, st_));
+        EAGEN_CUDA(cudaMemcpyAsync(pts, dp, n * 96, cudaMemcpyDeviceToHost, st_));
+        sync_check();
+    }
+
+    ResultImpl* divisor_host(const uint64_t* pts, size_t n, uint32_t flags, uint64_t* out_point) override {
+        use();
+        std::unique_ptr<ResultImpl> res(new ResultImpl());
+        res->device = dev_; res->n = n;
+        if (n == 0) {  // reference: :455 -> (from_const(1), identity)
+            res->nf = 1; res->a_stride = 1; res->b_stride = 1;
+            F one = F::one();
+            EAGEN_CUDA(cudaMemcpyAsync(res->A.ensure(32), &one, 32, cudaMemcpyHostToDevice, st_));
+            res->B.ensure(32);
+            res->la = {1}; res->lb = {0};
+            if (out_point) std::memset(out_point, 0, 64);
+            sync_check();
+            return res.release();
+        }
+        F* dp = (F*)in_points_.ensure(n * 96);
+        EAGEN_CUDA(cudaMemcpyAsync(dp, pts, n * 96, cudaMemcpyHostToDevice, st_));
+        EAGEN_CUDA(cudaEventRecord(ev0_, st_));
+        Aff* T = (Aff*)tpts_.ensure(n * sizeof(Aff));
+        F* zs = (F*)den_.ensure(n * 32);
+        launch(k_jac_z<FB>, n, 256, dp, n, zs);
+        batch_invert(zs, n);
+        launch(k_jac_to_affine<FB>, n, 256, (const F*)dp, (const F*)zs, n, T);
+        std::vector<int> cnt{(int)n};
+        Aff root;
+        std::vector<Aff> roots(1);
+        run_trees(T, n, cnt, flags, res.get(), 0, 1, roots.data());
+        EAGEN_CUDA(cudaEventRecord(ev1_, st_));
+        sync_check();
+        root = roots[0];
+        if (out_point) std::memcpy(out_point, &root, 64);
+        if (!(flags & EAGEN_PARTIAL) && !root.is_identity())
+            throw StatusError{EAGEN_E_SUM_NONZERO, "compute_divisor_witness: points do not sum to the identity"};
+        float ms = 0; EAGEN_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+        res->device_ms = ms;
+        return res.release();
+    }
+
+    void poly_mul_host(const uint64_t* a, size_t la, const uint64_t* b, size_t lb, uint64_t* out) override {
+        use();
+        if (la + lb == 0) return;
+        size_t len = la + lb - 1;
+        if (la == 0 || lb == 0) { std::memset(out, 0, len * 32); return; }  // mul_naive with one empty operand (:54-62)
+        int t = std::max(1, ceil_log2(len));
+        if ((unsigned)t > FB::S) throw StatusError{EAGEN_E_NTT_TOO_LARGE, "polynomial product longer than 2^S"};
+        size_t T = (size_t)1 << t;
+        F* da = (F*)ea_.ensure(T * 32); F* db = (F*)eb_.ensure(T * 32);
+        F* ca = (F*)oa_.ensure(std::max(la, len) * 32); F* cb = (F*)ob_.ensure(lb * 32);
+        EAGEN_CUDA(cudaMemcpyAsync(ca, a, la * 32, cudaMemcpyHostToDevice, st_));
+        EAGEN_CUDA(cudaMemcpyAsync(cb, b, lb * 32, cudaMemcpyHostToDevice, st_));
+        ensure_twiddles(t);
+        ntt(false, da, ca, la, (int)la, nullptr, 0, 0, t, 1, d_one_, 1);
+        ntt(false, db, cb, lb, (int)lb, nullptr, 0, 0, t, 1, d_one_, 1);
+        launch(k_mul_scale<FB>, T, 256, da, (const F*)db, T, half_pow(t));
+        ntt(true, da, nullptr, 0, 0, ca, len, (int)len, t, 1, d_one_, 1);
+        EAGEN_CUDA(cudaMemcpyAsync(out, ca, len * 32, cudaMemcpyDeviceToHost, st_));
+        sync_check();
+    }
+
+    void ntt_host(uint64_t* data, uint32_t log_n, int inverse) override {
+        use();
+        if (log_n > FB::S) throw StatusError{EAGEN_E_NTT_TOO_LARGE, "log_n exceeds the field's two-adicity"};
+        size_t T = (size_t)1 << log_n;
+        if (log_n == 0) return;
+        // best_fft is natural order in and out; the kernels are DIF (natural->bit-reversed) / DIT (bit-reversed->natural),
+        // so the helper permutes on the host (this entry point is an API helper, not on the hot path)
+        std::vector<uint64_t> tmp(T * 4);
+        auto brev = [&](size_t i) { size_t r = 0; for (uint32_t b = 0; b < log_n; ++b) r |= ((i >> b) & 1) << (log_n - 1 - b); return r; };
+        F* dd = (F*)ea_.ensure(T * 32);
+        ensure_twiddles((int)log_n);
+        if (!inverse) {
+            EAGEN_CUDA(cudaMemcpyAsync(dd, data, T * 32, cudaMemcpyHostToDevice, st_));
+            ntt(false, dd, nullptr, 0, 0, nullptr, 0, 0, (int)log_n, 1, d_one_, 1);
+            EAGEN_CUDA(cudaMemcpyAsync(tmp.data(), dd, T * 32, cudaMemcpyDeviceToHost, st_));
+            sync_check();
+            for (size_t i = 0; i < T; ++i) std::memcpy(data + 4 * brev(i), &tmp[4 * i], 32);
+        } else {
+            for (size_t i = 0; i < T; ++i) std::memcpy(&tmp[4 * i], data + 4 * brev(i), 32);
+            EAGEN_CUDA(cudaMemcpyAsync(dd, tmp.data(), T * 32, cudaMemcpyHostToDevice, st_));
+            ntt(true, dd, nullptr, 0, 0, nullptr, 0, 0, (int)log_n, 1, d_one_, 1);
+            EAGEN_CUDA(cudaMemcpyAsync(data, dd, T * 32, cudaMemcpyDeviceToHost, st_));
+            sync_check();
+        }
+    }
+
+    void batch_invert_host(uint64_t* elems, size_t n) override {
+        use();
+        if (!n) return;
+        F* dd = (F*)den_.ensure(n * 32);
+        EAGEN_CUDA(cudaMemcpyAsync(dd, elems, n * 32, cudaMemcpyHostToDevice, st_));
+        batch_invert(dd, n);
+        EAGEN_CUDA(cudaMemcpyAsync(elems, dd, n * 32, cudaMemcpyDeviceToHost, st_));
+        sync_check();
+    }
+
+    void eval_host(const uint64_t* a, size_t la, const uint64_t* b, size_t lb, const uint64_t* pts, size_t n, uint64_t* out) override {
+        use();
+        if (!n) return;
+        F* da = (F*)oa_.ensure(std::max<size_t>(la, 1) * 32); F* db = (F*)ob_.ensure(std::max<size_t>(lb, 1) * 32);
+        F* dp = (F*)in_points_.ensure(n * 96);
+        Aff* T = (Aff*)tpts_.ensure(n * sizeof(Aff));
+        F* zs = (F*)den_.ensure(n * 32);
+        if (la) EAGEN_CUDA(cudaMemcpyAsync(da, a, la * 32, cudaMemcpyHostToDevice, st_));
+        if (lb) EAGEN_CUDA(cudaMemcpyAsync(db, b, lb * 32, cudaMemcpyHostToDevice, st_));
+        EAGEN_CUDA(cudaMemcpyAsync(dp, pts, n * 96, cudaMemcpyHostToDevice, st_));
+        launch(k_jac_z<FB>, n, 256, (const F*)dp, n, zs);
+        batch_invert(zs, n);
+        launch(k_jac_to_affine<FB>, n, 256, (const F*)dp, (const F*)zs, n, T);
+        launch(k_eval_function<FB>, n, 128, (const F*)da, (int)la, (const F*)db, (int)lb, (const Aff*)T, n, zs);
+        EAGEN_CUDA(cudaMemcpyAsync(out, zs, n * 32, cudaMemcpyDeviceToHost, st_));
+        sync_check();
+    }
+
+private:
+    int dev_;
+    cudaStream_t st_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    int* d_err_ = nullptr;
+    int* d_one_ = nullptr;
+    uint64_t launches_ = 0;
+    int tw_max_ = 0;
+    DevBuf tw_fwd_, tw_inv_;
+    DevBuf in_scalars_, in_points_, planes_, rows_, table_, sums_, partials_, carries_, carries_proj_;
+    DevBuf cnt_, tree_n_, tree_of_pos_, tpts_;
+    DevBuf ptlev_, lvlcnt_, a_[2], b_[2], ea_, eb_, oa_, ob_, den_, binv_, desc_, tops_, lead_;
+
+    void use() { EAGEN_CUDA(cudaSetDevice(dev_)); }
+
+    template <class K, class... Args>
+    void launch(K kernel, size_t work, int threads, Args... args) {
+        if (work == 0) return;
+        size_t blocks = (work + threads - 1) / threads;
+        kernel<<<(unsigned)blocks, threads, 0, st_>>>(args...);
+        ++launches_;
+        EAGEN_CUDA(cudaGetLastError());
+    }
+    template <class K, class... Args>
+    void launch2d(K kernel, dim3 grid, int threads, Args... args) {
+        if (grid.x == 0 || grid.y == 0) return;
+        kernel<<<grid, threads, 0, st_>>>(args...);
+        ++launches_;
+        EAGEN_CUDA(cudaGetLastError());
+    }
+
+    void sync_check() {
+        EAGEN_CUDA(cudaStreamSynchronize(st_));
+        int e = 0;
+        EAGEN_CUDA(cudaMemcpy(&e, d_err_, sizeof(int), cudaMemcpyDeviceToHost));
+        if (e) {
+            EAGEN_CUDA(cudaMemset(d_err_, 0, sizeof(int)));
+            if (e & KERR_RANGE) throw StatusError{EAGEN_E_RANGE, "scalar out of range: must be < isqrt(order)+2"};
+            if (e & KERR_DIGITS) throw StatusError{EAGEN_E_DIGITS, "negbase expansion does not fit in d digits"};
+            throw StatusError{EAGEN_E_DOMAIN, "an intermediate point's x-coordinate lies on the evaluation domain"};
+        }
+    }
+
+    static F half_pow(int t) {
+        F r = F::one(), h = F::two_inv();
+        for (int i = 0; i < t; ++i) r = mul(r, h);
+        return r;
+    }
+
+    void ensure_twiddles(int t) {
+        if (t <= tw_max_) return;
+        if ((unsigned)t > FB::S) throw StatusError{EAGEN_E_NTT_TOO_LARGE, "transform size exceeds the field's two-adicity"};
+        size_t cnt = (size_t)1 << t;
+        F* f = (F*)tw_fwd_.ensure(cnt * 32);
+        F* i = (F*)tw_inv_.ensure(cnt * 32);
+        launch(k_gen_twiddles<FB>, cnt, 256, f, t, 0);
+        launch(k_gen_twiddles<FB>, cnt, 256, i, t, 1);
+        tw_max_ = t;
+    }
+    const F* tw(bool inverse, int t) { return (inverse ? tw_inv_.as<F>() : tw_fwd_.as<F>()) + ((size_t)1 << (t - 1)); }
+
+    // in-place batched inversion of M elements (zeros stay zero)
+    void batch_invert(F* x, size_t M) {
+        if (M == 0) return;
+        // level sizes
+        std::vector<size_t> sz{M};
+        while (sz.back() > 1024) sz.push_back((sz.back() + BINV_G - 1) / BINV_G);
+        size_t scratch = 0;
+        for (size_t l = 0; l + 1 < sz.size(); ++l) scratch += sz[l] + sz[l + 1];
+        F* s = (F*)binv_.ensure(std::max<size_t>(scratch, 1) * 32);
+        std::vector<F*> xs{x}, prefs;
+        F* cur = s;
+        for (size_t l = 0; l + 1 < sz.size(); ++l) { prefs.push_back(cur); cur += sz[l]; xs.push_back(cur); cur += sz[l + 1]; }
+        for (size_t l = 0; l + 1 < sz.size(); ++l)
+            launch(k_binv_up<FB>, sz[l + 1], 128, (const F*)xs[l], prefs[l], xs[l + 1], sz[l], sz[l + 1]);
+        launch(k_binv_base<FB>, sz.back(), 64, xs.back(), sz.back());
+        for (size_t l = sz.size() - 1; l-- > 0;)
+            launch(k_binv_down<FB>, sz[l + 1], 128, xs[l], (const F*)prefs[l], (const F*)xs[l + 1], sz[l], sz[l + 1]);
+    }
+
+    // batched transform of n_tr arrays of size 2^t living in `data`; optional compact gather / scatter
+    void ntt(bool inverse, F* data, const F* src, size_t src_stride, int src_len, F* dst, size_t dst_stride, int dst_len,
+             int t, size_t n_tr, const int* counts, int node_max) {
+        NttPass<FB> a;
+        a.data = data; a.tw = tw(inverse, t); a.counts = counts; a.node_max = node_max;
+        a.total = n_tr << t; a.t = t;
+        a.src_stride = src_stride; a.src_len = src_len; a.dst_stride = dst_stride; a.dst_len = dst_len;
+        std::vector<std::pair<int, int>> plan = ntt_plan(t);
+        if (inverse) std::reverse(plan.begin(), plan.end());
+        size_t tiles = (a.total + NTT_TILE - 1) / NTT_TILE;
+        for (size_t p = 0; p < plan.size(); ++p) {
+            a.s_hi = plan[p].first; a.s_lo = plan[p].second;
+            a.src = (p == 0) ? src : nullptr;
+            a.dst = (p + 1 == plan.size()) ? dst : nullptr;
+            if (inverse) k_ntt_pass<FB, true><<<(unsigned)tiles, NTT_THREADS, 0, st_>>>(a);
+            else k_ntt_pass<FB, false><<<(unsigned)tiles, NTT_THREADS, 0, st_>>>(a);
+            ++launches_;
+            EAGEN_CUDA(cudaGetLastError());
+        }
+    }
+
+    void run_negbase(const Fe<FS>* ds, size_t n, const NegbaseParams& prm, uint8_t* planes, uint8_t* rows) {
+        launch(k_negbase<FS>, n, 128, ds, n, prm, planes, rows, d_err_);
+    }
+
+    void run_multiples(const F* dp, size_t n, uint8_t base, Aff* tab) {
+        size_t m = n * (size_t)(base - 1);
+        if (m == 0) return;
+        F* zs = (F*)den_.ensure(m * 32);
+        launch(k_multiples_proj<CC>, n, 128, dp, n, (uint32_t)base, tab, zs);
+        batch_invert(zs, m);
+        launch(k_scale_by_zinv<FB>, m, 256, tab, (const F*)zs, m);
+    }
+
+    void run_shard_sums(const Fe<FS>* ds, const F* dp, size_t n, const NegbaseParams& prm, uint8_t* planes, uint8_t* rows, Aff* tab, Prj* sums) {
+        const uint32_t d = prm.d;
+        if (n) {
+            run_negbase(ds, n, prm, planes, rows);
+            run_multiples(dp, n, (uint8_t)prm.base, tab);
+        }
+        int per_thread = 32;
+        size_t chunk = (size_t)SUMS_THREADS * per_thread;
+        int chunks = (int)std::max<size_t>(1, (n + chunk - 1) / chunk);
+        Prj* partials = (Prj*)partials_.ensure((size_t)d * chunks * sizeof(Prj));
+        launch2d(k_digit_sums<CC>, dim3(chunks, d), SUMS_THREADS, (const uint8_t*)planes, (const Aff*)tab, n, prm.base, per_thread, partials);
+        launch2d(k_reduce_partials<CC>, dim3(d, 1), SUMS_THREADS, (const Prj*)partials, chunks, sums);
+    }
+
+    void run_carry_chain(const Prj* sums, int nparts, uint32_t d, uint8_t base, Aff* carries) {
+        Prj* cp = (Prj*)carries_proj_.ensure((size_t)d * sizeof(Prj));
+        F* zs = (F*)lead_.ensure((size_t)d * 32);
+        launch(k_carry_chain<CC>, 1, 32, sums, d, (uint32_t)base, nparts, cp, zs);
+        batch_invert(zs, d);
+        launch(k_proj_to_affine<FB>, d, 64, (const Prj*)cp, (const F*)zs, (size_t)d, carries);
+    }
+
+    // divisor witnesses for iteration positions [pos_begin, pos_end); function index k = d-1-pos (ret.reverse(), :132)
+    void run_position_trees(const uint8_t* planes, const Aff* tab, const Aff* carries, size_t n, uint8_t base, uint32_t d,
+                            uint32_t pos_begin, uint32_t pos_end, uint32_t flags, ResultImpl* res) {
+        const uint32_t npos = pos_end - pos_begin;
+        if (npos == 0) return;
+        int chunks = (int)std::max<size_t>(1, (n + CHUNK_PTS - 1) / CHUNK_PTS);
+        int* cnt = (int*)cnt_.ensure((size_t)d * chunks * sizeof(int));
+        int* tree_n = (int*)tree_n_.ensure((size_t)d * sizeof(int));
+        launch2d(k_count_nonzero, dim3(chunks, d), 256, planes, n, chunks, cnt);
+        launch(k_scan_chunks<FB>, d, 64, cnt, chunks, d, (uint32_t)base, carries, tree_n);
+        std::vector<int> hn(d);
+        EAGEN_CUDA(cudaMemcpyAsync(hn.data(), tree_n, (size_t)d * sizeof(int), cudaMemcpyDeviceToHost, st_));
+        EAGEN_CUDA(cudaStreamSynchronize(st_));
+        size_t nmax = 1;
+        for (uint32_t p = pos_begin; p < pos_end; ++p) nmax = std::max<size_t>(nmax, (size_t)hn[p]);
+        // result slots sized for the deepest tree of the range
+        int Lmax = ceil_log2((nmax + 1) / 2);
+        res->nf = npos;
+        res->a_stride = ((size_t)1 << Lmax) + 1;
+        res->b_stride = std::max<size_t>((size_t)1 << Lmax, 1);
+        res->A.ensure(res->nf * res->a_stride * 32);
+        res->B.ensure(res->nf * res->b_stride * 32);
+        res->la.assign(npos, 0); res->lb.assign(npos, 0);
+        // group positions so that one group's working set fits the memory budget
+        size_t free_b = 0, total_b = 0;
+        EAGEN_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        size_t per_tree = tree_bytes(nmax);
+        size_t budget = (size_t)((double)(free_b + pooled_bytes()) * 0.80);
+        uint32_t group = (uint32_t)std::max<size_t>(1, std::min<size_t>(npos, budget / std::max<size_t>(per_tree, 1)));
+        int* tree_of_pos = (int*)tree_of_pos_.ensure((size_t)d * sizeof(int));
+        std::vector<Aff> roots(npos);
+        for (uint32_t g0 = pos_begin; g0 < pos_end; g0 += group) {
+            uint32_t g1 = std::min(pos_end, g0 + group), nt = g1 - g0;
+            std::vector<int> map(d, -1), cnts(nt);
+            for (uint32_t p = g0; p < g1; ++p) { map[p] = (int)(p - g0); cnts[p - g0] = hn[p]; }
+            EAGEN_CUDA(cudaMemcpyAsync(tree_of_pos, map.data(), (size_t)d * sizeof(int), cudaMemcpyHostToDevice, st_));
+            EAGEN_CUDA(cudaStreamSynchronize(st_));  // `map` is a stack temporary
+            Aff* T = (Aff*)tpts_.ensure((size_t)nt * nmax * sizeof(Aff));
+            launch2d(k_scatter_points<FB>, dim3(chunks, d), 256, planes, tab, n, (uint32_t)base, (const int*)cnt, chunks, carries,
+                     (const int*)tree_n, (const int*)tree_of_pos, T, nmax);
+            // result slot of position p is k = d-1-p; within this result handle slots are relative to the range:
+            // slot = (pos_end-1-p), so slot 0 is the highest position of the range (= lowest k)
+            run_trees(T, nmax, cnts, flags, res, /*first slot*/ pos_end - g1, /*reverse*/ -1, roots.data() + (g0 - pos_begin));
+        }
+        sync_check();
+        for (uint32_t i = 0; i < npos; ++i)
+            if (!roots[i].is_identity()) throw StatusError{EAGEN_E_SUM_NONZERO, "internal: a digit position's points do not sum to the identity"};
+    }
+
+    size_t pooled_bytes() const {
+        return tpts_.cap + ptlev_.cap + a_[0].cap + a_[1].cap + b_[0].cap + b_[1].cap + ea_.cap + eb_.cap + oa_.cap + ob_.cap + den_.cap + binv_.cap + desc_.cap;
+    }
+    // working-set estimate per tree of n points (bytes)
+    static size_t tree_bytes(size_t n) {
+        size_t lc = (n + 1) / 2;
+        size_t L = (size_t)ceil_log2(lc);
+        size_t pad = lc + ((size_t)1 << L) + 8;  // slack for the +1 slots and the top levels
+        return n * 64 + 2 * lc * 64 + pad * 32 * (4 + 4 + 2 + 3) + lc * sizeof(MergeDesc<FB>) / 2 + 4096;
+    }
+
+    // Divisor witnesses of `nt` point lists (T + tree*cap, counts cnts[tree]) -> res slots.
+    // slot(tree) = first_slot + (dir > 0 ? tree : nt-1-tree).  roots[tree] receives the root output point.
+    void run_trees(const Aff* T, size_t cap, const std::vector<int>& cnts, uint32_t flags, ResultImpl* res, size_t first_slot, int dir, Aff* roots) {
+        const int nt = (int)cnts.size();
+        size_t nmax = 0;
+        for (int c : cnts) nmax = std::max<size_t>(nmax, (size_t)c);
+        if (nmax == 0) throw StatusError{EAGEN_E_EMPTY, "divisor witness of an empty point list"};
+        if (res->nf == 0) {  // stand-alone call: size the result here
+            int Lm = ceil_log2((nmax + 1) / 2);
+            res->nf = nt; res->a_stride = ((size_t)1 << Lm) + 1; res->b_stride = std::max<size_t>((size_t)1 << Lm, 1);
+            res->A.ensure(res->nf * res->a_stride * 32); res->B.ensure(res->nf * res->b_stride * 32);
+            res->la.assign(nt, 0); res->lb.assign(nt, 0);
+        }
+        const size_t lc_max = (nmax + 1) / 2;
+        const int L = ceil_log2(lc_max);
+        if ((unsigned)L + 1 > FB::S) throw StatusError{EAGEN_E_NTT_TOO_LARGE, "tree too deep for the field's two-adicity"};
+        std::vector<size_t> node_max(L + 1);
+        node_max[0] = lc_max;
+        for (int l = 1; l <= L; ++l) node_max[l] = (node_max[l - 1] + 1) / 2;
+        // per-level, per-tree node counts; row 0 of the table is the point count itself
+        std::vector<int> lv((size_t)(L + 2) * nt);
+        for (int tr = 0; tr < nt; ++tr) {
+            lv[tr] = cnts[tr];
+            int c = (cnts[tr] + 1) / 2;
+            for (int l = 0; l <= L; ++l) { lv[(size_t)(l + 1) * nt + tr] = c; c = (c + 1) / 2; }
+        }
+        int* dlv = (int*)lvlcnt_.ensure(lv.size() * sizeof(int));
+        EAGEN_CUDA(cudaMemcpyAsync(dlv, lv.data(), lv.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+        EAGEN_CUDA(cudaStreamSynchronize(st_));
+        auto cnt_of = [&](int level) { return (const int*)(dlv + (size_t)(level + 1) * nt); };
+
+        // memory plan
+        size_t pt_total = 0, szA = 0, szB = 0, szE = 0, szO = 0;
+        std::vector<size_t> pt_off(L + 1);
+        for (int l = 0; l <= L; ++l) {
+            pt_off[l] = pt_total; pt_total += (size_t)nt * node_max[l];
+            size_t m = (size_t)1 << l;
+            szA = std::max(szA, (size_t)nt * node_max[l] * (m + 1));
+            szB = std::max(szB, (size_t)nt * node_max[l] * m);
+            if (l < L) {
+                szE = std::max(szE, (size_t)nt * node_max[l] * 2 * m);
+                szO = std::max(szO, (size_t)nt * node_max[l + 1] * 2 * m);
+            }
+        }
+        Aff* PT = (Aff*)ptlev_.ensure(pt_total * sizeof(Aff));
+        F* A[2] = {(F*)a_[0].ensure(szA * 32), (F*)a_[1].ensure(szA * 32)};
+        F* B[2] = {(F*)b_[0].ensure(szB * 32), (F*)b_[1].ensure(szB * 32)};
+        F* EA = (F*)ea_.ensure(std::max<size_t>(szE, 1) * 32); F* EB = (F*)eb_.ensure(std::max<size_t>(szE, 1) * 32);
+        F* OA = (F*)oa_.ensure(std::max<size_t>(szO, 1) * 32); F* OB = (F*)ob_.ensure(std::max<size_t>(szO, 1) * 32);
+        F* den = (F*)den_.ensure(std::max<size_t>(std::max(szO, (size_t)nt * node_max[0]), 1) * 32);
+        MergeDesc<FB>* desc = (MergeDesc<FB>*)desc_.ensure(std::max<size_t>((size_t)nt * (L ? node_max[1] : 1), 1) * sizeof(MergeDesc<FB>));
+        if (L) ensure_twiddles(L);
+
+        // level 0: outputs -(P+Q) and the line functions
+        size_t w0 = (size_t)nt * node_max[0];
+        launch(k_pair_den<FB>, w0, 256, T, cap, (const int*)dlv, node_max[0], nt, den);
+        batch_invert(den, w0);
+        launch(k_pair_finish<FB>, w0, 256, T, cap, (const int*)dlv, node_max[0], nt, (const F*)den, 1, PT + pt_off[0]);
+        launch(k_leaf_lines<FB>, w0, 256, T, cap, (const int*)dlv, (const Aff*)(PT + pt_off[0]), node_max[0], nt, A[0], B[0]);
+
+        int cur = 0;
+        for (int l = 0; l < L; ++l) {
+            const int t = l + 1;
+            const size_t m = (size_t)1 << l, Tn = 2 * m;
+            const size_t nodes = node_max[l], merges = node_max[l + 1];
+            const size_t wm = (size_t)nt * merges;
+            Aff* Pc = PT + pt_off[l];
+            Aff* Pp = PT + pt_off[l + 1];
+            // output points of the parents and the merge descriptors
+            launch(k_pair_den<FB>, wm, 256, (const Aff*)Pc, nodes, cnt_of(l), merges, nt, den);
+            batch_invert(den, wm);
+            launch(k_pair_finish<FB>, wm, 256, (const Aff*)Pc, nodes, cnt_of(l), merges, nt, (const F*)den, 0, Pp);
+            F tinv = half_pow(t);
+            launch(k_merge_desc<FB>, wm, 128, (const Aff*)Pc, nodes, cnt_of(l), (const Aff*)Pp, merges, nt, tinv, desc);
+            // children -> evaluation domain
+            ntt(false, EA, A[cur], m + 1, (int)(m + 1), nullptr, 0, 0, t, (size_t)nt * nodes, cnt_of(l), (int)nodes);
+            ntt(false, EB, B[cur], m, (int)m, nullptr, 0, 0, t, (size_t)nt * nodes, cnt_of(l), (int)nodes);
+            // pointwise merge with exact division
+            launch(k_den<FB>, wm << t, 256, (const MergeDesc<FB>*)desc, wm, t, tw(false, t), den, d_err_);
+            batch_invert(den, wm << t);
+            launch(k_pointwise<CC>, wm << t, 128, (const MergeDesc<FB>*)desc, wm, t, tw(false, t), tinv, (const F*)EA, (const F*)EB,
+                   (const F*)den, merges, nodes, OA, OB);
+            // back to coefficients, compact parent slots
+            ntt(true, OA, nullptr, 0, 0, A[cur ^ 1], Tn + 1, (int)Tn, t, wm, cnt_of(l + 1), (int)merges);
+            ntt(true, OB, nullptr, 0, 0, B[cur ^ 1], Tn, (int)Tn, t, wm, cnt_of(l + 1), (int)merges);
+            launch(k_fixup<FB>, wm, 128, (const MergeDesc<FB>*)desc, wm, t, merges, nodes, (const F*)A[cur], (const F*)B[cur], A[cur ^ 1]);
+            cur ^= 1;
+        }
+        // roots: one node per tree at level L (node_max[L] == 1)
+        const size_t ra = ((size_t)1 << L) + 1, rb = (size_t)1 << L;
+        int* tops = (int*)tops_.ensure((size_t)2 * nt * sizeof(int));
+        EAGEN_CUDA(cudaMemsetAsync(tops, 0, (size_t)2 * nt * sizeof(int), st_));
+        launch2d(k_find_top<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, (const F*)A[cur], ra, (int)ra, tops);
+        launch2d(k_find_top<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, (const F*)B[cur], rb, (int)rb, tops + nt);
+        if (!(flags & EAGEN_RAW_TREE)) {
+            F* lead = (F*)lead_.ensure((size_t)std::max(nt, 1) * 32);
+            launch(k_lead<FB>, nt, 64, (const F*)A[cur], ra, (const int*)tops, (const F*)B[cur], rb, (const int*)(tops + nt), nt, lead);
+            batch_invert(lead, nt);
+            launch2d(k_scale<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, A[cur], ra, (const int*)tops, (const F*)lead);
+            launch2d(k_scale<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, B[cur], rb, (const int*)(tops + nt), (const F*)lead);
+        }
+        // scatter into the result slots
+        std::vector<int> htops((size_t)2 * nt);
+        EAGEN_CUDA(cudaMemcpyAsync(htops.data(), tops, htops.size() * sizeof(int), cudaMemcpyDeviceToHost, st_));
+        EAGEN_CUDA(cudaMemcpyAsync(roots, PT + pt_off[L], (size_t)nt * sizeof(Aff), cudaMemcpyDeviceToHost, st_));
+        for (int tr = 0; tr < nt; ++tr) {
+            size_t slot = first_slot + (dir > 0 ? (size_t)tr : (size_t)(nt - 1 - tr));
+            EAGEN_CUDA(cudaMemcpyAsync(res->A.as<F>() + slot * res->a_stride, A[cur] + (size_t)tr * ra, ra * 32, cudaMemcpyDeviceToDevice, st_));
+            EAGEN_CUDA(cudaMemcpyAsync(res->B.as<F>() + slot * res->b_stride, B[cur] + (size_t)tr * rb, rb * 32, cudaMemcpyDeviceToDevice, st_));
+        }
+        EAGEN_CUDA(cudaStreamSynchronize(st_));
+        for (int tr = 0; tr < nt; ++tr) {
+            size_t slot = first_slot + (dir > 0 ? (size_t)tr : (size_t)(nt - 1 - tr));
+            res->la[slot] = htops[tr]; res->lb[slot] = htops[nt + tr];
+        }
+    }
+};
+
+IEngine* make_engine_pallas(int device);
+IEngine* make_engine_vesta(int device);
+IEngine* make_engine_grumpkin(int device);
+
+}  // namespace eagen

@@ -1,0 +1,860 @@
+// Hand-written sm_100a kernels for the Liam-Eagen MSM witness hot path.
+//
+// Kernel map (K-numbers as in SURVEY.md section 2.2), reference semantics each one replaces:
+//   K1  k_negbase            negbase_decompose + pad + reverse     src/negbase_utils.rs:20-36, src/argument_witness_calc.rs:93-101
+//   K2  k_multiples_*        precompute_multiplicities (affine)    src/argument_witness_calc.rs:43-51,103
+//   K3  k_digit_sums, k_reduce_partials   the carry += mult[j][digit] loop   src/argument_witness_calc.rs:120-125
+//   K4  k_carry_chain        carry = (-carry)*base + S_i           src/argument_witness_calc.rs:105-127
+//   K5  k_pair_den/finish, k_leaf_lines, k_merge_desc   from_pair / from_point / linefunc / output points
+//                                                                    src/regular_functions_utils.rs:285-331,335
+//   K6  k_ntt_pass           Polynomial::mul_fft -> best_fft        src/regular_functions_utils.rs:102-129
+//   K7  k_den, k_pointwise, k_fixup   RegularFunction::mul, Propagation::merge, kate_div   :266-273,333-360,45-47
+//   K9  k_binv_*             z.invert() (batched, Montgomery trick) :351-352
+//   K10 k_find_top, k_lead, k_scale   trim + monic canonical form    SURVEY.md section 8c
+//
+// All kernels are integer-pipe (IMAD/IADD3) or HBM bound; none is a dense contraction, so no tcgen05.
+#pragma once
+#include <cuda_runtime.h>
+#include "curve.cuh"
+
+namespace eagen {
+
+// ------------------------------------------------------------------------------------------------
+// 128-bit vectorised element access
+// ------------------------------------------------------------------------------------------------
+template <class FP>
+EAGEN_D Fe<FP> ldg(const Fe<FP>* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    Fe<FP> r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+template <class FP>
+EAGEN_D void stg(Fe<FP>* p, const Fe<FP>& r) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+template <class FP>
+EAGEN_D Affine<FP> ldg_aff(const Affine<FP>* p) {
+    Affine<FP> a;
+    a.x = ldg(&p->x);
+    a.y = ldg(&p->y);
+    return a;
+}
+template <class FP>
+EAGEN_D void stg_aff(Affine<FP>* p, const Affine<FP>& a) {
+    stg(&p->x, a.x);
+    stg(&p->y, a.y);
+}
+
+// error flag bits written by kernels (device int, OR-ed)
+enum : int {
+    KERR_RANGE = 1,        // scalar >= isqrt(order)+2            (reference: src/argument_witness_calc.rs:97)
+    KERR_DIGITS = 2,       // negbase expansion needs more than d digits (reference truncates silently, :99)
+    KERR_COLLISION = 4,    // an output point's x-coordinate is a 2^k-th root of unity of the evaluation domain
+};
+
+// ------------------------------------------------------------------------------------------------
+// K9  batched inversion (Montgomery trick), hierarchical: each thread owns G strided elements
+// ------------------------------------------------------------------------------------------------
+constexpr int BINV_G = 16;
+
+template <class FP>
+__global__ void k_binv_up(const Fe<FP>* __restrict__ x, Fe<FP>* __restrict__ pref, Fe<FP>* __restrict__ tot, size_t M, size_t Tn) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Tn) return;
+    Fe<FP> acc = Fe<FP>::one();
+#pragma unroll 1
+    for (int j = 0; j < BINV_G; ++j) {
+        size_t idx = t + (size_t)j * Tn;
+        if (idx >= M) break;
+        Fe<FP> v = ldg(x + idx);
+        if (!v.is_zero()) acc = mul(acc, v);
+        stg(pref + idx, acc);
+    }
+    stg(tot + t, acc);
+}
+
+template <class FP>
+__global__ void k_binv_down(Fe<FP>* __restrict__ x, const Fe<FP>* __restrict__ pref, const Fe<FP>* __restrict__ tot, size_t M, size_t Tn) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Tn) return;
+    Fe<FP> it = ldg(tot + t);
+#pragma unroll 1
+    for (int j = BINV_G - 1; j >= 0; --j) {
+        size_t idx = t + (size_t)j * Tn;
+        if (idx >= M) continue;
+        Fe<FP> v = ldg(x + idx);
+        if (v.is_zero()) continue;
+        Fe<FP> prev = j > 0 ? ldg(pref + idx - Tn) : Fe<FP>::one();
+        stg(x + idx, mul(it, prev));
+        it = mul(it, v);
+    }
+}
+
+template <class FP>
+__global__ void k_binv_base(Fe<FP>* x, size_t M) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M) return;
+    stg(x + t, inv(ldg(x + t)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1  negabase digits.  x = sum d_i (-b)^i  <=>  the ordinary base-b digits e_i of y = x + K with
+// K = sum_{odd i<d} (b-1) b^i satisfy d_i = e_i (i even), d_i = b-1-e_i (i odd).  One thread per scalar,
+// 128-bit loads, chunked long division by b^c < 2^32.
+// ------------------------------------------------------------------------------------------------
+struct NegbaseParams {
+    uint32_t sq[8];      // isqrt(order)+2 (canonical limbs)
+    uint32_t K[8];       // offset constant
+    uint32_t bd[8];      // b^d
+    uint32_t base, d, chunk_digits, chunk;  // chunk = base^chunk_digits < 2^32
+};
+
+EAGEN_HD bool lt8(const uint32_t* a, const uint32_t* b) {
+    for (int i = 7; i >= 0; --i) {
+        if (a[i] != b[i]) return a[i] < b[i];
+    }
+    return false;
+}
+
+template <class FS>
+__global__ void k_negbase(const Fe<FS>* __restrict__ scalars, size_t n, NegbaseParams prm, uint8_t* __restrict__ planes /* d x n */,
+                          uint8_t* __restrict__ rows /* n x d or null */, int* err) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    Fe<FS> x = to_canonical(ldg(scalars + j));
+    if (!lt8(x.v, prm.sq)) { atomicOr(err, KERR_RANGE); return; }
+    uint32_t y[8];
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c += (uint64_t)x.v[i] + prm.K[i]; y[i] = (uint32_t)c; c >>= 32; }
+    if (!lt8(y, prm.bd)) { atomicOr(err, KERR_DIGITS); return; }
+    const uint32_t d = prm.d, base = prm.base;
+    int top = 7;
+    while (top > 0 && y[top] == 0) --top;
+    uint32_t i = 0;
+    while (i < d) {
+        uint64_t rem = 0;
+        for (int l = top; l >= 0; --l) {
+            uint64_t cur = (rem << 32) | y[l];
+            y[l] = (uint32_t)(cur / prm.chunk);
+            rem = cur % prm.chunk;
+        }
+        while (top > 0 && y[top] == 0) --top;
+        uint32_t r = (uint32_t)rem;
+        for (uint32_t k = 0; k < prm.chunk_digits && i < d; ++k, ++i) {
+            uint32_t e = r % base;
+            r /= base;
+            uint32_t dg = (i & 1) ? (base - 1 - e) : e;
+            uint32_t pos = d - 1 - i;  // MSD first
+            planes[(size_t)pos * n + j] = (uint8_t)dg;
+            if (rows) rows[j * d + pos] = (uint8_t)dg;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  small multiples [P, 2P, ..., (b-1)P], affine after one batched inversion of the Z's
+// ------------------------------------------------------------------------------------------------
+template <class CC>
+__global__ void k_multiples_proj(const Fe<typename CC::Base>* __restrict__ jac /* n x 3 */, size_t n, uint32_t base,
+                                 Affine<typename CC::Base>* __restrict__ table /* n x (b-1): X,Y for now */,
+                                 Fe<typename CC::Base>* __restrict__ zs) {
+    typedef typename CC::Base F;
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    Proj<F> p = jacobian_to_proj<CC>(ldg(jac + 3 * j), ldg(jac + 3 * j + 1), ldg(jac + 3 * j + 2));
+    Proj<F> acc = p;
+    for (uint32_t k = 1; k < base; ++k) {
+        size_t o = j * (base - 1) + (k - 1);
+        stg(&table[o].x, acc.x);
+        stg(&table[o].y, acc.y);
+        stg(zs + o, acc.z);
+        if (k + 1 < base) acc = padd<CC>(acc, p);
+    }
+}
+
+// (X, Y) *= 1/Z ; Z == 0 -> identity (0,0).  zs holds the inverses (0 where Z was 0).
+template <class FP>
+__global__ void k_scale_by_zinv(Affine<FP>* __restrict__ pts, const Fe<FP>* __restrict__ zinv, size_t m) {
+    size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= m) return;
+    Fe<FP> zi = ldg(zinv + o);
+    Affine<FP> a;
+    if (zi.is_zero()) a = Affine<FP>::identity();
+    else { a.x = mul(ldg(&pts[o].x), zi); a.y = mul(ldg(&pts[o].y), zi); }
+    stg_aff(pts + o, a);
+}
+
+// Jacobian (X,Y,Z) -> affine (X/Z^2, Y/Z^3), two kernels around one batched inversion
+template <class FP>
+__global__ void k_jac_z(const Fe<FP>* __restrict__ jac, size_t n, Fe<FP>* __restrict__ zs) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) stg(zs + j, ldg(jac + 3 * j + 2));
+}
+template <class FP>
+__global__ void k_jac_to_affine(const Fe<FP>* __restrict__ jac, const Fe<FP>* __restrict__ zinv, size_t n, Affine<FP>* __restrict__ out) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    Fe<FP> zi = ldg(zinv + j);
+    Affine<FP> a;
+    if (zi.is_zero()) a = Affine<FP>::identity();
+    else {
+        Fe<FP> zi2 = sqr(zi);
+        a.x = mul(ldg(jac + 3 * j), zi2);
+        a.y = mul(ldg(jac + 3 * j + 1), mul(zi2, zi));
+    }
+    stg_aff(out + j, a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3  per digit position i:  S_i = sum_j table[j][D[i][j]-1]   (complete mixed additions)
+// grid = (chunks, d); each thread walks `per_thread` points strided by blockDim
+// ------------------------------------------------------------------------------------------------
+constexpr int SUMS_THREADS = 128;
+
+template <class CC>
+__global__ void __launch_bounds__(SUMS_THREADS)
+k_digit_sums(const uint8_t* __restrict__ planes, const Affine<typename CC::Base>* __restrict__ table, size_t n, uint32_t base,
+             int per_thread, Proj<typename CC::Base>* __restrict__ partials /* d x chunks */) {
+    typedef typename CC::Base F;
+    __shared__ Proj<F> sm[SUMS_THREADS];
+    const uint32_t pos = blockIdx.y;
+    const size_t chunk0 = (size_t)blockIdx.x * SUMS_THREADS * per_thread;
+    Proj<F> acc = Proj<F>::identity();
+    const uint8_t* dg = planes + (size_t)pos * n;
+    for (int k = 0; k < per_thread; ++k) {
+        size_t j = chunk0 + (size_t)k * SUMS_THREADS + threadIdx.x;
+        if (j >= n) break;
+        uint32_t dv = dg[j];
+        if (dv == 0) continue;
+        Affine<F> q = ldg_aff(table + j * (base - 1) + (dv - 1));
+        if (q.is_identity()) continue;
+        acc = padd_mixed<CC>(acc, q);
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = SUMS_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = padd<CC>(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[(size_t)pos * gridDim.x + blockIdx.x] = sm[0];
+}
+
+// one block per digit position: reduce `count` partial sums
+template <class CC>
+__global__ void __launch_bounds__(SUMS_THREADS)
+k_reduce_partials(const Proj<typename CC::Base>* __restrict__ partials, int count, Proj<typename CC::Base>* __restrict__ out) {
+    typedef typename CC::Base F;
+    __shared__ Proj<F> sm[SUMS_THREADS];
+    const uint32_t pos = blockIdx.x;
+    Proj<F> acc = Proj<F>::identity();
+    for (int k = threadIdx.x; k < count; k += SUMS_THREADS) acc = padd<CC>(acc, partials[(size_t)pos * count + k]);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = SUMS_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = padd<CC>(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[pos] = sm[0];
+}
+
+// K4  Horner chain in base (-b): carry_i = b * (-carry_{i-1}) + S_i ; serial in i (d steps)
+template <class CC>
+__global__ void k_carry_chain(const Proj<typename CC::Base>* __restrict__ sums, uint32_t d, uint32_t base, int nparts,
+                              Proj<typename CC::Base>* __restrict__ carries /* d */, Fe<typename CC::Base>* __restrict__ zs /* d */) {
+    typedef typename CC::Base F;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Proj<F> carry = Proj<F>::identity();
+    int hb = 31 - __clz(base);
+    for (uint32_t i = 0; i < d; ++i) {
+        Proj<F> nc = pneg<CC>(carry);
+        Proj<F> acc = nc;  // top bit of base
+        for (int bit = hb - 1; bit >= 0; --bit) {
+            acc = pdbl<CC>(acc);
+            if ((base >> bit) & 1) acc = padd<CC>(acc, nc);
+        }
+        // sums may come as several per-rank partials (multi-GPU all-gather): sums[part*d + i]
+        for (int part = 0; part < nparts; ++part) acc = padd<CC>(acc, sums[(size_t)part * d + i]);
+        carry = acc;
+        carries[i] = carry;
+        stg(zs + i, carry.z);
+    }
+}
+
+template <class FP>
+__global__ void k_proj_to_affine(const Proj<FP>* __restrict__ p, const Fe<FP>* __restrict__ zinv, size_t n, Affine<FP>* __restrict__ out) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    Proj<FP> q = p[j];
+    stg_aff(out + j, proj_to_affine(q, ldg(zinv + j)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Building tmp_i (reference: src/argument_witness_calc.rs:110-127) for every digit position at once:
+//   T_i = [-carry_{i-1}] x base (if carry_{i-1} != O)  ++  [table[j][D[i][j]-1] : D[i][j] != 0, j ascending]  ++  [-carry_i]
+// stream compaction = count per 1024-point chunk, scan of chunk counts, scatter.
+// ------------------------------------------------------------------------------------------------
+constexpr int CHUNK_PTS = 1024;
+
+static __global__ void k_count_nonzero(const uint8_t* __restrict__ planes, size_t n, int chunks, int* __restrict__ cnt /* d x chunks */) {
+    const uint32_t pos = blockIdx.y;
+    const size_t j0 = (size_t)blockIdx.x * CHUNK_PTS;
+    int c = 0;
+    for (int k = threadIdx.x; k < CHUNK_PTS; k += blockDim.x) {
+        size_t j = j0 + k;
+        if (j < n && planes[(size_t)pos * n + j] != 0) ++c;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ int sm[32];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sm[w];
+        cnt[(size_t)pos * chunks + blockIdx.x] = s;
+    }
+}
+
+// one thread per digit position: exclusive scan of its chunk counts (chunks is small: n/1024)
+template <class FP>
+__global__ void k_scan_chunks(int* __restrict__ cnt, int chunks, uint32_t d, uint32_t base, const Affine<FP>* __restrict__ carries,
+                              int* __restrict__ tree_n /* d */) {
+    uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= d) return;
+    int off = 0;
+    if (pos > 0 && !ldg_aff(carries + pos - 1).is_identity()) off = (int)base;
+    int* c = cnt + (size_t)pos * chunks;
+    for (int k = 0; k < chunks; ++k) { int v = c[k]; c[k] = off; off += v; }
+    tree_n[pos] = off + 1;  // + the closing -carry_i
+}
+
+template <class FP>
+__global__ void k_scatter_points(const uint8_t* __restrict__ planes, const Affine<FP>* __restrict__ table, size_t n, uint32_t base,
+                                 const int* __restrict__ offs, int chunks, const Affine<FP>* __restrict__ carries,
+                                 const int* __restrict__ tree_n, const int* __restrict__ tree_of_pos /* d: slot or -1 */,
+                                 Affine<FP>* __restrict__ T, size_t cap) {
+    const uint32_t pos = blockIdx.y;
+    const int slot = tree_of_pos[pos];
+    if (slot < 0) return;
+    Affine<FP>* out = T + (size_t)slot * cap;
+    __shared__ int warp_tot[32];
+    const size_t j0 = (size_t)blockIdx.x * CHUNK_PTS;
+    int run = offs[(size_t)pos * chunks + blockIdx.x];
+    // CHUNK_PTS / blockDim rounds, each an intra-block exclusive scan of the keep flags
+    for (int k0 = 0; k0 < CHUNK_PTS; k0 += blockDim.x) {
+        size_t j = j0 + k0 + threadIdx.x;
+        uint32_t dv = j < n ? planes[(size_t)pos * n + j] : 0;
+        unsigned keep = dv != 0;
+        unsigned bal = __ballot_sync(0xffffffffu, keep);
+        int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        int before = __popc(bal & ((1u << lane) - 1));
+        if (lane == 0) warp_tot[wid] = __popc(bal);
+        __syncthreads();
+        int wbase = 0, tot = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { int v = warp_tot[w]; if (w < wid) wbase += v; tot += v; }
+        if (keep) stg_aff(out + run + wbase + before, ldg_aff(table + j * (base - 1) + (dv - 1)));
+        run += tot;
+        __syncthreads();
+    }
+    if (blockIdx.x == 0 && threadIdx.x < base + 1) {
+        if (threadIdx.x < base) {
+            if (pos > 0) {
+                Affine<FP> c = ldg_aff(carries + pos - 1);
+                if (!c.is_identity()) stg_aff(out + threadIdx.x, aneg(c));
+            }
+        } else {
+            stg_aff(out + tree_n[pos] - 1, aneg(ldg_aff(carries + pos)));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5  pairwise affine sums with one batched inversion per level.
+//   mode 0 (leaves): in = T (points), pair (2k, 2k+1), result = -(P+Q)
+//   mode 1 (merges): in = outputs of the level below, result = A + B
+// A missing / identity partner needs no inversion (den = 0 is skipped by the batch inverter).
+// ------------------------------------------------------------------------------------------------
+template <class FP>
+EAGEN_D Fe<FP> pair_den(const Affine<FP>& p, const Affine<FP>& q) {
+    if (p.is_identity() || q.is_identity()) return Fe<FP>::zero();
+    if (p.x == q.x) {
+        if (p.y == q.y) return dbl(p.y);  // tangent (y != 0 on a prime-order curve)
+        return Fe<FP>::zero();            // P + (-P)
+    }
+    return sub(q.x, p.x);
+}
+template <class FP>
+EAGEN_D Affine<FP> pair_sum(const Affine<FP>& p, const Affine<FP>& q, const Fe<FP>& dinv) {
+    if (p.is_identity()) return q;
+    if (q.is_identity()) return p;
+    Fe<FP> lam;
+    if (p.x == q.x) {
+        if (!(p.y == q.y)) return Affine<FP>::identity();
+        Fe<FP> xx = sqr(p.x);
+        lam = mul(add(dbl(xx), xx), dinv);
+    } else {
+        lam = mul(sub(q.y, p.y), dinv);
+    }
+    Affine<FP> r;
+    r.x = sub(sub(sqr(lam), p.x), q.x);
+    r.y = sub(mul(lam, sub(p.x, r.x)), p.y);
+    return r;
+}
+
+// tree-batched addressing: element (tree, idx) of a level lives at tree*stride + idx; idx valid below cnt[tree]
+template <class FP>
+__global__ void k_pair_den(const Affine<FP>* __restrict__ in, size_t in_stride, const int* __restrict__ in_cnt,
+                           size_t out_stride, int ntrees, Fe<FP>* __restrict__ den) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= out_stride * ntrees) return;
+    int tree = (int)(g / out_stride);
+    size_t k = g % out_stride;
+    int c = in_cnt[tree];
+    Fe<FP> dv = Fe<FP>::zero();
+    if ((long long)(2 * k + 1) < c) dv = pair_den(ldg_aff(in + tree * in_stride + 2 * k), ldg_aff(in + tree * in_stride + 2 * k + 1));
+    stg(den + g, dv);
+}
+
+template <class FP>
+__global__ void k_pair_finish(const Affine<FP>* __restrict__ in, size_t in_stride, const int* __restrict__ in_cnt,
+                              size_t out_stride, int ntrees, const Fe<FP>* __restrict__ dinv, int negate,
+                              Affine<FP>* __restrict__ out) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= out_stride * ntrees) return;
+    int tree = (int)(g / out_stride);
+    size_t k = g % out_stride;
+    int c = in_cnt[tree];
+    if ((long long)(2 * k) >= c) return;
+    Affine<FP> p = ldg_aff(in + tree * in_stride + 2 * k);
+    Affine<FP> q = (long long)(2 * k + 1) < c ? ldg_aff(in + tree * in_stride + 2 * k + 1) : Affine<FP>::identity();
+    Affine<FP> s = pair_sum(p, q, ldg(dinv + g));
+    stg_aff(out + g, negate ? aneg(s) : s);
+}
+
+// line through affine a, b as (lx, ly, lz) = cross((ax,ay,1),(bx,by,1)); tangent fallback through c = -(a+b)
+// (reference: src/regular_functions_utils.rs:285-303 with z = 1; identity = (0,0,0))
+template <class FP>
+EAGEN_D void line_coeffs(const Affine<FP>& a, const Affine<FP>& b, const Affine<FP>& c, Fe<FP>& lx, Fe<FP>& ly, Fe<FP>& lz) {
+    const bool ai = a.is_identity(), bi = b.is_identity();
+    Fe<FP> az = ai ? Fe<FP>::zero() : Fe<FP>::one(), bz = bi ? Fe<FP>::zero() : Fe<FP>::one();
+    lz = sub(mul(a.x, b.y), mul(a.y, b.x));
+    lx = ai ? (bi ? Fe<FP>::zero() : neg(b.y)) : (bi ? a.y : sub(a.y, b.y));   // ay*bz - az*by
+    ly = ai ? (bi ? Fe<FP>::zero() : Fe<FP>::zero()) : (bi ? Fe<FP>::zero() : sub(b.x, a.x));  // az*bx - ax*bz
+    if (ai && !bi) ly = Fe<FP>::zero();
+    (void)az; (void)bz;
+    if (!lx.is_zero() || !ly.is_zero() || !lz.is_zero()) return;
+    const bool ci = c.is_identity();
+    lz = sub(mul(a.x, c.y), mul(a.y, c.x));
+    lx = ai ? (ci ? Fe<FP>::zero() : neg(c.y)) : (ci ? a.y : sub(a.y, c.y));
+    ly = (ai || ci) ? Fe<FP>::zero() : sub(c.x, a.x);
+}
+
+// level-0 functions: a = [lz, lx], b = [ly]; both points identity -> the constant 1
+// (reference: Propagation::from_pair / from_point / empty, src/regular_functions_utils.rs:319-331)
+template <class FP>
+__global__ void k_leaf_lines(const Affine<FP>* __restrict__ T, size_t t_stride, const int* __restrict__ t_cnt,
+                             const Affine<FP>* __restrict__ outp, size_t out_stride, int ntrees,
+                             Fe<FP>* __restrict__ A /* stride 2 */, Fe<FP>* __restrict__ B /* stride 1 */) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= out_stride * ntrees) return;
+    int tree = (int)(g / out_stride);
+    size_t k = g % out_stride;
+    int c = t_cnt[tree];
+    if ((long long)(2 * k) >= c) return;
+    Affine<FP> p = ldg_aff(T + tree * t_stride + 2 * k);
+    Affine<FP> q = (long long)(2 * k + 1) < c ? ldg_aff(T + tree * t_stride + 2 * k + 1) : Affine<FP>::identity();
+    Fe<FP> lx, ly, lz;
+    if (p.is_identity() && q.is_identity()) {
+        lz = Fe<FP>::one(); lx = Fe<FP>::zero(); ly = Fe<FP>::zero();
+    } else {
+        if (p.is_identity()) { p = q; q = Affine<FP>::identity(); }  // from_pair(O, Q) = from_point(Q)
+        if (q.is_identity()) q = aneg(p);                             // from_point(P) = line(P, -P)
+        line_coeffs(p, q, ldg_aff(outp + g), lx, ly, lz);
+    }
+    stg(A + 2 * g, lz);
+    stg(A + 2 * g + 1, lx);
+    stg(B + g, ly);
+}
+
+// per-merge descriptor for the level that joins children (2j, 2j+1)
+enum : uint32_t { MERGE_ABSENT = 0, MERGE_PASS = 1, MERGE_SHORTCUT = 2, MERGE_GENERIC = 3 };
+
+template <class FP>
+struct MergeDesc {
+    Fe<FP> alpha, beta;       // x of the children's outputs (division roots)
+    Fe<FP> lz, lx, ly;        // line(-A, -B), unscaled   (l0 + l1 x + l2 y = lz + lx x + ly y)
+    Fe<FP> slz, slx, sly;     // same, times 1/T (folds the inverse-transform scaling into the product)
+    uint32_t mode, pad[3];
+};
+
+template <class FP>
+__global__ void k_merge_desc(const Affine<FP>* __restrict__ child, size_t child_stride, const int* __restrict__ child_cnt,
+                             const Affine<FP>* __restrict__ parent, size_t parent_stride, int ntrees, Fe<FP> tinv,
+                             MergeDesc<FP>* __restrict__ desc) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= parent_stride * ntrees) return;
+    int tree = (int)(g / parent_stride);
+    size_t j = g % parent_stride;
+    int c = child_cnt[tree];
+    MergeDesc<FP> dsc;
+    dsc.pad[0] = dsc.pad[1] = dsc.pad[2] = 0;
+    dsc.alpha = dsc.beta = dsc.lz = dsc.lx = dsc.ly = dsc.slz = dsc.slx = dsc.sly = Fe<FP>::zero();
+    if ((long long)(2 * j) >= c) dsc.mode = MERGE_ABSENT;
+    else if ((long long)(2 * j + 1) >= c) dsc.mode = MERGE_PASS;
+    else {
+        Affine<FP> a = ldg_aff(child + tree * child_stride + 2 * j), b = ldg_aff(child + tree * child_stride + 2 * j + 1);
+        if (a.is_identity() || b.is_identity()) dsc.mode = MERGE_SHORTCUT;
+        else {
+            dsc.mode = MERGE_GENERIC;
+            dsc.alpha = a.x; dsc.beta = b.x;
+            line_coeffs(aneg(a), aneg(b), ldg_aff(parent + g), dsc.lx, dsc.ly, dsc.lz);
+            dsc.slz = mul(dsc.lz, tinv); dsc.slx = mul(dsc.lx, tinv); dsc.sly = mul(dsc.ly, tinv);
+        }
+    }
+    desc[g] = dsc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6  batched radix-2 NTT, shared-memory passes of up to 10 stages over 1024-element tiles.
+//   forward : decimation in frequency, natural order in -> bit-reversed order out
+//   inverse : decimation in time, bit-reversed in -> natural order out, unscaled (1/T is folded into K7)
+// The whole batch is one flat array of n_transforms * T elements; a pass covers stages [s_lo, s_hi].
+// The first forward pass can gather from compact coefficient slots (zero padding), the last inverse
+// pass can scatter back into compact slots, so no separate pad / copy kernels touch HBM.
+// ------------------------------------------------------------------------------------------------
+constexpr int NTT_TILE_LOG = 10;
+constexpr int NTT_TILE = 1 << NTT_TILE_LOG;
+constexpr int NTT_THREADS = 256;
+
+template <class FP>
+struct NttPass {
+    Fe<FP>* data;            // workspace, n_transforms * T
+    const Fe<FP>* src;       // optional compact source (first forward pass)
+    Fe<FP>* dst;             // optional compact destination (last inverse pass)
+    const Fe<FP>* tw;        // tw[e] = w_T^e (or w_T^-e), e < T/2
+    const int* counts;       // transforms present per tree
+    size_t total;            // n_transforms * T
+    size_t src_stride, dst_stride;
+    int src_len, dst_len;
+    int node_max;            // transforms per tree (stride of the tree index)
+    int t, s_hi, s_lo;
+};
+
+EAGEN_D uint32_t insert_zero_bit(uint32_t v, int pos) {
+    uint32_t lo = v & ((1u << pos) - 1);
+    return ((v >> pos) << (pos + 1)) | lo;
+}
+
+template <class FP, bool INVERSE>
+__global__ void __launch_bounds__(NTT_THREADS)
+k_ntt_pass(NttPass<FP> a) {
+    __shared__ uint4 sm[NTT_TILE * 2];
+    Fe<FP>* s = reinterpret_cast<Fe<FP>*>(sm);
+    const int k = a.s_hi - a.s_lo + 1;
+    const int lw = NTT_TILE_LOG - k;
+    const size_t tile = blockIdx.x;
+    const size_t Tmask = ((size_t)1 << a.t) - 1;
+
+    size_t lin[4];
+    bool live[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        uint32_t q = r * NTT_THREADS + threadIdx.x;
+        uint32_t E, wl;
+        if (a.s_lo == 0) { E = q & ((1u << k) - 1); wl = q >> k; }
+        else { wl = q & ((1u << lw) - 1); E = q >> lw; }
+        size_t w = (tile << lw) + wl;
+        size_t L = w & (((size_t)1 << a.s_lo) - 1), H = w >> a.s_lo;
+        lin[r] = (H << (a.s_hi + 1)) | ((size_t)E << a.s_lo) | L;
+        live[r] = lin[r] < a.total;
+        Fe<FP> v = Fe<FP>::zero();
+        if (live[r]) {
+            size_t tr = lin[r] >> a.t;
+            int tree = (int)(tr / a.node_max), node = (int)(tr % a.node_max);
+            live[r] = node < a.counts[tree];
+            if (live[r]) {
+                size_t i = lin[r] & Tmask;
+                if (a.src) { if ((int)i < a.src_len) v = ldg(a.src + tr * a.src_stride + i); }
+                else v = ldg(a.data + lin[r]);
+            }
+        }
+        s[(E << lw) | wl] = v;
+    }
+    __syncthreads();
+
+    for (int st = 0; st < k; ++st) {
+        const int sigma = INVERSE ? st : (k - 1 - st);   // local stage
+        const int sg = a.s_lo + sigma;                   // global stage
+        const int bitpos = sigma + lw;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            uint32_t bq = r * NTT_THREADS + threadIdx.x;
+            uint32_t i0 = insert_zero_bit(bq, bitpos), i1 = i0 | (1u << bitpos);
+            uint32_t E = i0 >> lw, wl = i0 & ((1u << lw) - 1);
+            size_t w = (tile << lw) + wl;
+            size_t L = w & (((size_t)1 << a.s_lo) - 1);
+            size_t j = ((size_t)(E & ((1u << sigma) - 1)) << a.s_lo) | L;
+            Fe<FP> wj = ldg(a.tw + (j << (a.t - 1 - sg)));
+            Fe<FP> u = s[i0], v = s[i1];
+            if (INVERSE) {
+                v = mul(v, wj);
+                s[i0] = add(u, v);
+                s[i1] = sub(u, v);
+            } else {
+                s[i0] = add(u, v);
+                s[i1] = mul(sub(u, v), wj);
+            }
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (!live[r]) continue;
+        uint32_t q = r * NTT_THREADS + threadIdx.x;
+        uint32_t E, wl;
+        if (a.s_lo == 0) { E = q & ((1u << k) - 1); wl = q >> k; }
+        else { wl = q & ((1u << lw) - 1); E = q >> lw; }
+        Fe<FP> v = s[(E << lw) | wl];
+        if (a.dst) {
+            size_t tr = lin[r] >> a.t, i = lin[r] & Tmask;
+            if ((int)i < a.dst_len) stg(a.dst + tr * a.dst_stride + i, v);
+        } else {
+            stg(a.data + lin[r], v);
+        }
+    }
+}
+
+// w_T^e tables for every size up to 2^tmax:  tab[2^(t-1) + e] = w_{2^t}^e, e < 2^(t-1)
+template <class FP>
+__global__ void k_gen_twiddles(Fe<FP>* __restrict__ tab, int tmax, int inverse) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0 || idx >= ((size_t)1 << tmax)) return;
+    int t = 64 - __clzll((unsigned long long)idx);   // idx in [2^(t-1), 2^t)
+    size_t e = idx - ((size_t)1 << (t - 1));
+    Fe<FP> w = omega_for<FP>((unsigned)t, inverse != 0);
+    Fe<FP> r = Fe<FP>::one();
+    for (int bit = t - 2; bit >= 0; --bit) {
+        r = sqr(r);
+        if ((e >> bit) & 1) r = mul(r, w);
+    }
+    stg(tab + idx, r);
+}
+
+// evaluation point stored at position p of a forward transform of size 2^t
+template <class FP>
+EAGEN_D Fe<FP> eval_point(const Fe<FP>* __restrict__ tw, int t, uint32_t p) {
+    uint32_t kx = t ? (__brev(p) >> (32 - t)) : 0;
+    uint32_t half = 1u << (t - 1);
+    if (kx < half) return ldg(tw + kx);
+    return neg(ldg(tw + (kx - half)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7  merge in the evaluation domain.  Children (a1 + y b1), (a2 + y b2), line l = lz + lx x + ly y,
+// g(x) = x^3 + b:
+//   (a2 + y b2) * l      = U + y V,   U = a2*lam + b2*ly*g,  V = a2*ly + b2*lam,  lam = lz + lx x
+//   (a1 + y b1)(U + y V) = (a1 U + b1 V g) + y (a1 V + b1 U)
+// then / ((x - alpha)(x - beta)) pointwise (reference: src/regular_functions_utils.rs:266-273,344-357).
+// ------------------------------------------------------------------------------------------------
+template <class FP>
+__global__ void k_den(const MergeDesc<FP>* __restrict__ desc, size_t nmerges, int t, const Fe<FP>* __restrict__ tw,
+                      Fe<FP>* __restrict__ den, int* err) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (nmerges << t)) return;
+    size_t m = g >> t;
+    uint32_t p = (uint32_t)(g & (((size_t)1 << t) - 1));
+    Fe<FP> dv = Fe<FP>::zero();
+    if (desc[m].mode == MERGE_GENERIC) {
+        Fe<FP> x = eval_point(tw, t, p);
+        dv = mul(sub(x, ldg(&desc[m].alpha)), sub(x, ldg(&desc[m].beta)));
+        if (dv.is_zero()) atomicOr(err, KERR_COLLISION);
+    }
+    stg(den + g, dv);
+}
+
+template <class CC>
+__global__ void k_pointwise(const MergeDesc<typename CC::Base>* __restrict__ desc, size_t nmerges, int t,
+                            const Fe<typename CC::Base>* __restrict__ tw, Fe<typename CC::Base> tinv,
+                            const Fe<typename CC::Base>* __restrict__ EA, const Fe<typename CC::Base>* __restrict__ EB,
+                            const Fe<typename CC::Base>* __restrict__ dinv, size_t merges_per_tree, size_t nodes_per_tree,
+                            Fe<typename CC::Base>* __restrict__ OA, Fe<typename CC::Base>* __restrict__ OB) {
+    typedef typename CC::Base F;
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (nmerges << t)) return;
+    size_t m = g >> t;
+    uint32_t p = (uint32_t)(g & (((size_t)1 << t) - 1));
+    uint32_t mode = desc[m].mode;
+    if (mode == MERGE_ABSENT) return;
+    size_t tree = m / merges_per_tree, j = m % merges_per_tree;
+    size_t c1 = ((tree * nodes_per_tree + 2 * j) << t) + p, c2 = c1 + ((size_t)1 << t);
+    Fe<F> a1 = ldg(EA + c1), b1 = ldg(EB + c1);
+    Fe<F> ra, rb;
+    if (mode == MERGE_PASS) {
+        ra = mul(a1, tinv); rb = mul(b1, tinv);
+    } else {
+        Fe<F> a2 = ldg(EA + c2), b2 = ldg(EB + c2);
+        Fe<F> x = eval_point(tw, t, p);
+        Fe<F> gx = add(mul(sqr(x), x), CC::b());
+        if (mode == MERGE_SHORTCUT) {
+            a1 = mul(a1, tinv); b1 = mul(b1, tinv);
+            ra = add(mul(a1, a2), mul(mul(b1, b2), gx));
+            rb = add(mul(a1, b2), mul(b1, a2));
+        } else {
+            Fe<F> lam = add(ldg(&desc[m].slz), mul(ldg(&desc[m].slx), x));
+            Fe<F> ly = ldg(&desc[m].sly);
+            Fe<F> lyg = mul(ly, gx);
+            Fe<F> U = add(mul(a2, lam), mul(b2, lyg));
+            Fe<F> V = add(mul(a2, ly), mul(b2, lam));
+            Fe<F> di = ldg(dinv + g);
+            ra = mul(add(mul(a1, U), mul(mul(b1, gx), V)), di);
+            rb = mul(add(mul(a1, V), mul(b1, U)), di);
+        }
+    }
+    stg(OA + g, ra);
+    stg(OB + g, rb);
+}
+
+// The parent's a has T+1 coefficients but the transform has T points: the top coefficient q_T aliases
+// onto coefficient 0.  q_T has a closed form in the children's top coefficients, so compute it, subtract it
+// from coefficient 0 and store it at index T.
+template <class FP>
+__global__ void k_fixup(const MergeDesc<FP>* __restrict__ desc, size_t nmerges, int t, size_t merges_per_tree, size_t nodes_per_tree,
+                        const Fe<FP>* __restrict__ A, const Fe<FP>* __restrict__ B /* children, slots m+1 / m */,
+                        Fe<FP>* __restrict__ PA /* parent a, slot T+1 */) {
+    size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= nmerges) return;
+    uint32_t mode = desc[m].mode;
+    if (mode == MERGE_ABSENT) return;
+    const size_t T = (size_t)1 << t, h = T >> 1;  // children: a has h+1 coefficients, b has h
+    Fe<FP>* pa = PA + m * (T + 1);
+    Fe<FP> q = Fe<FP>::zero();
+    if (mode != MERGE_PASS) {
+        size_t tree = m / merges_per_tree, j = m % merges_per_tree;
+        size_t n1 = tree * nodes_per_tree + 2 * j, n2 = n1 + 1;
+        const Fe<FP>* a1 = A + n1 * (h + 1); const Fe<FP>* a2 = A + n2 * (h + 1);
+        const Fe<FP>* b1 = B + n1 * h; const Fe<FP>* b2 = B + n2 * h;
+        Fe<FP> a1t = ldg(a1 + h), a2t = ldg(a2 + h), b1t = ldg(b1 + h - 1), b2t = ldg(b2 + h - 1);
+        if (mode == MERGE_GENERIC) {
+            // x^(T+2) coefficient of the numerator's a-part = b1t b2t lx + (a1t b2t + b1t a2t) ly
+            q = add(mul(mul(b1t, b2t), ldg(&desc[m].lx)), mul(add(mul(a1t, b2t), mul(b1t, a2t)), ldg(&desc[m].ly)));
+        } else {
+            // x^T coefficient of a1 a2 + b1 b2 (x^3 + b)
+            q = mul(a1t, a2t);
+            if (h >= 2) q = add(q, add(mul(b1t, ldg(b2 + h - 2)), mul(ldg(b1 + h - 2), b2t)));
+        }
+    }
+    stg(pa, sub(ldg(pa), q));
+    stg(pa + T, q);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10  canonical form: trim trailing zeros, divide by the coefficient of highest pole order
+// ------------------------------------------------------------------------------------------------
+template <class FP>
+__global__ void k_find_top(const Fe<FP>* __restrict__ coef, size_t stride, int len, int* __restrict__ top /* per tree, init 0 */) {
+    int tree = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    if (!ldg(coef + (size_t)tree * stride + i).is_zero()) atomicMax(top + tree, i + 1);
+}
+
+template <class FP>
+__global__ void k_lead(const Fe<FP>* __restrict__ A, size_t sa, const int* __restrict__ topa, const Fe<FP>* __restrict__ B, size_t sb,
+                       const int* __restrict__ topb, int ntrees, Fe<FP>* __restrict__ lead) {
+    int tree = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tree >= ntrees) return;
+    int la = topa[tree], lb = topb[tree];
+    long oa = la ? 2L * (la - 1) : -1, ob = lb ? 2L * (lb - 1) + 3 : -1;
+    Fe<FP> l = Fe<FP>::zero();
+    if (la || lb) l = oa > ob ? ldg(A + (size_t)tree * sa + la - 1) : ldg(B + (size_t)tree * sb + lb - 1);
+    stg(lead + tree, l);
+}
+
+template <class FP>
+__global__ void k_scale(Fe<FP>* __restrict__ coef, size_t stride, const int* __restrict__ top, const Fe<FP>* __restrict__ linv) {
+    int tree = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= top[tree]) return;
+    Fe<FP>* c = coef + (size_t)tree * stride + i;
+    stg(c, mul(ldg(c), ldg(linv + tree)));
+}
+
+// gather root functions of several trees into per-position result slots
+template <class FP>
+__global__ void k_copy_strided(const Fe<FP>* __restrict__ src, size_t src_stride, Fe<FP>* __restrict__ dst, size_t dst_stride, int len) {
+    int tree = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    stg(dst + (size_t)tree * dst_stride + i, ldg(src + (size_t)tree * src_stride + i));
+}
+
+// pointwise product with scaling for the stand-alone polynomial product (Polynomial::mul_fft, :119-127)
+template <class FP>
+__global__ void k_mul_scale(Fe<FP>* __restrict__ a, const Fe<FP>* __restrict__ b, size_t n, Fe<FP> sc) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) stg(a + i, mul(mul(ldg(a + i), ldg(b + i)), sc));
+}
+
+// evaluate a(x) + y b(x) at many affine points: one thread per point, Horner (RegularFunction::ev, :228-237)
+template <class FP>
+__global__ void k_eval_function(const Fe<FP>* __restrict__ A, int la, const Fe<FP>* __restrict__ B, int lb,
+                                const Affine<FP>* __restrict__ pts, size_t n, Fe<FP>* __restrict__ out) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    Affine<FP> p = ldg_aff(pts + j);
+    Fe<FP> va = Fe<FP>::zero(), vb = Fe<FP>::zero();
+    for (int i = la - 1; i >= 0; --i) va = add(mul(va, p.x), ldg(A + i));
+    for (int i = lb - 1; i >= 0; --i) vb = add(mul(vb, p.x), ldg(B + i));
+    stg(out + j, add(va, mul(vb, p.y)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Synthetic inputs for tests and bench.py: scalars uniform in [0, 2^127) from SplitMix64,
+// points P_j = (a + j*b) * G for seed-derived 64-bit a, b (distinct points, no structure a kernel could exploit),
+// emitted as Jacobian triples with non-trivial z.
+// ------------------------------------------------------------------------------------------------
+EAGEN_HD uint64_t splitmix64(uint64_t& s) {
+    s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+template <class CC>
+__global__ void k_synth_inputs(uint64_t seed, size_t n, Fe<typename CC::Scalar>* __restrict__ scalars, Fe<typename CC::Base>* __restrict__ jac) {
+    typedef typename CC::Base F;
+    typedef typename CC::Scalar S;
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint64_t st = seed ^ (0xD1B54A32D192ED03ull * (j + 1));
+    uint64_t lo = splitmix64(st), hi = splitmix64(st) >> 1;  // 127 bits
+    Fe<S> sc = Fe<S>::zero();
+    sc.v[0] = (uint32_t)lo; sc.v[1] = (uint32_t)(lo >> 32); sc.v[2] = (uint32_t)hi; sc.v[3] = (uint32_t)(hi >> 32);
+    stg(scalars + j, from_canonical(sc));
+    uint64_t s2 = seed;
+    uint64_t a = splitmix64(s2) | 1, b = splitmix64(s2) | 1;
+    // k = a + j*b as a 128-bit integer
+    unsigned long long klo = a + (unsigned long long)j * b;
+    unsigned long long khi = __umul64hi((unsigned long long)j, b) + (klo < a ? 1ull : 0ull);
+    Affine<F> g; g.x = CC::gx(); g.y = CC::gy();
+    Proj<F> acc = Proj<F>::identity();
+    for (int bit = 127; bit >= 0; --bit) {
+        acc = pdbl<CC>(acc);
+        unsigned long long w = bit >= 64 ? khi : klo;
+        if ((w >> (bit & 63)) & 1) acc = padd_mixed<CC>(acc, g);
+    }
+    // homogeneous (x : y : z) -> Jacobian (x z, y z^2, z)
+    Fe<F> zz = sqr(acc.z);
+    stg(jac + 3 * j, mul(acc.x, acc.z));
+    stg(jac + 3 * j + 1, mul(acc.y, zz));
+    stg(jac + 3 * j + 2, acc.z);
+}
+
+}  // namespace eagen

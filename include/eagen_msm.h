@@ -1,0 +1,165 @@
+/* eagen_msm.h -- C ABI of the B200-native Liam-Eagen MSM witness engine (libeagen_msm.so).
+ *
+ * This is the drop-in boundary for the witness hot path of levs57/halo2-liam-eagen-msm.  The reference has no
+ * FFI today: its "operator API" is the set of public Rust functions below; each entry point here is what a thin
+ * Rust shim binds to keep those signatures (see INTEGRATION.md and halo2-liam-eagen-msm_b200/rust/).
+ *
+ * Data layout (identical to the in-memory form of halo2curves / pasta_curves types):
+ *   field element : 32 bytes, little endian, MONTGOMERY residue (R = 2^256) = Rust `[u64; 4]`
+ *                   (reference reinterprets the same bytes: src/precomputed_fft_data.rs:72)
+ *   Jacobian point: x | y | z, 3 field elements (96 bytes); identity has z = 0
+ *                   (what CurveExt::jacobian_coordinates() returns, src/regular_functions_utils.rs:229,427)
+ *   affine point  : x | y, 2 field elements (64 bytes); the identity is encoded as (0, 0)
+ *   digits        : u8, n x d row-major, most significant digit first
+ *                   (digits_by_scalar after the reverse, src/argument_witness_calc.rs:99-101)
+ *
+ * All functions return EAGEN_OK (0) or a negative error code; nothing here ever falls back to a CPU path.
+ * A context is bound to one CUDA device and is not thread-safe (use one context per thread).
+ */
+#ifndef EAGEN_MSM_H
+#define EAGEN_MSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct eagen_ctx eagen_ctx;
+typedef struct eagen_result eagen_result;
+
+enum eagen_curve {
+    EAGEN_CURVE_PALLAS = 0,   /* base Fp, scalars Fq, y^2 = x^3 + 5 */
+    EAGEN_CURVE_VESTA = 1,    /* base Fq, scalars Fp, y^2 = x^3 + 5 */
+    EAGEN_CURVE_GRUMPKIN = 2  /* base bn256::Fr, y^2 = x^3 - 17: the curve the reference's tests instantiate */
+};
+
+enum eagen_status {
+    EAGEN_OK = 0,
+    EAGEN_E_ARG = -1,           /* null pointer, unknown curve, base < 2 ...                                      */
+    EAGEN_E_LEN = -2,           /* "incompatible amount of coefficients"   src/argument_witness_calc.rs:88       */
+    EAGEN_E_RANGE = -3,         /* scalar >= isqrt(order)+2                src/argument_witness_calc.rs:97       */
+    EAGEN_E_SUM_NONZERO = -4,   /* points do not sum to the identity       src/regular_functions_utils.rs:478    */
+    EAGEN_E_NTT_TOO_LARGE = -5, /* F::S < loglength                        src/regular_functions_utils.rs:110    */
+    EAGEN_E_CUDA = -6,          /* CUDA runtime error (see eagen_last_error)                                     */
+    EAGEN_E_NCCL = -7,          /* reserved for the collective layer                                             */
+    EAGEN_E_DIGITS = -8,        /* negbase expansion longer than d digits (the reference truncates silently, :99) */
+    EAGEN_E_DOMAIN = -9,        /* an intermediate point's x lies on the power-of-two evaluation domain          */
+    EAGEN_E_NO_DEVICE = -10,    /* no CUDA device: there is deliberately no CPU fallback                         */
+    EAGEN_E_EMPTY = -11         /* group_merge of an empty list            src/regular_functions_utils.rs:382    */
+};
+
+/* flags for eagen_lhs_witness / eagen_divisor_witness */
+enum eagen_flags {
+    EAGEN_CANONICAL = 0,        /* default: trailing zeros trimmed, function monic in its highest-pole-order term */
+    EAGEN_RAW_TREE = 1,         /* reference tree order, every line built from z = 1 points, no final scaling;
+                                   trailing zero coefficients trimmed                                            */
+    EAGEN_PARTIAL = 2,          /* compute_divisor_witness_partial: do not require the points to sum to zero     */
+    EAGEN_NO_FUNCTIONS = 4,     /* digits + carries only (skips the divisor witnesses)                           */
+    EAGEN_KEEP_DIGITS = 8       /* also materialise the n x d digit matrix in the result                         */
+};
+
+/* which polynomial of a function a(x) + y b(x) */
+enum eagen_which { EAGEN_POLY_A = 0, EAGEN_POLY_B = 1 };
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+int eagen_ctx_create(int curve, int device, eagen_ctx** out);
+void eagen_ctx_destroy(eagen_ctx* ctx);
+const char* eagen_last_error(const eagen_ctx* ctx);   /* message of the last failing call (never NULL)        */
+const char* eagen_status_string(int status);
+/* number of kernels this context has launched so far (bench.py reports the per-step delta as gpu_launches) */
+uint64_t eagen_launch_count(const eagen_ctx* ctx);
+
+/* ---- host-side scalars of the path ---------------------------------------------------------------------
+ * order / isqrt / logb_ceil: d = logb_ceil(isqrt(order)+2, base) + 1      src/argument_witness_calc.rs:32-40,54-56,89-91 */
+int eagen_num_digits(int curve, uint8_t base, uint32_t* d);
+
+/* ---- the hot path, host buffers in / host buffers out ------------------------------------------------- */
+
+/* negbase_decompose + pad + reverse for n scalars            src/negbase_utils.rs:20-36, argument_witness_calc.rs:93-101
+ * scalars: n x 32 B Montgomery elements of the SCALAR field; digits: n x d bytes, MSD first.                */
+int eagen_negbase_decompose(eagen_ctx* ctx, const uint64_t* scalars, size_t n, uint8_t base, uint8_t* digits);
+
+/* precompute_multiplicities for n points                      src/argument_witness_calc.rs:43-51,103
+ * pts: n Jacobian points; out: n x (base-1) affine points, out[j][k-1] = k * P_j.                          */
+int eagen_precompute_multiplicities(eagen_ctx* ctx, const uint64_t* pts, size_t n, uint8_t base, uint64_t* out);
+
+/* compute_lhs_witness                                         src/argument_witness_calc.rs:87-136
+ * Returns a result handle holding the carry (= sum s_j P_j, affine), the d per-iteration carries and d functions;
+ * function k belongs to digit position k (the reference's ret after the reverse, :132).                    */
+int eagen_lhs_witness(eagen_ctx* ctx, const uint64_t* scalars, const uint64_t* pts, size_t n, uint8_t base,
+                      uint32_t flags, eagen_result** out);
+
+/* compute_divisor_witness / compute_divisor_witness_partial   src/regular_functions_utils.rs:453-480
+ * pts: n Jacobian points.  out_point (may be NULL): affine output point (-sum), 64 bytes.                   */
+int eagen_divisor_witness(eagen_ctx* ctx, const uint64_t* pts, size_t n, uint32_t flags, uint64_t* out_point,
+                          eagen_result** out);
+
+/* ---- result handle ------------------------------------------------------------------------------------ */
+uint32_t eagen_result_num_digits(const eagen_result* r);                    /* d                              */
+size_t eagen_result_num_functions(const eagen_result* r);
+size_t eagen_result_poly_len(const eagen_result* r, size_t k, int which);    /* coefficients in a_k or b_k     */
+int eagen_result_poly_copy(eagen_result* r, size_t k, int which, uint64_t* out);  /* len x 4 u64, low degree first */
+int eagen_result_carry(eagen_result* r, uint64_t* out_affine);              /* 64 bytes                       */
+int eagen_result_carries(eagen_result* r, uint64_t* out_affine);            /* d x 64 bytes, iteration order  */
+int eagen_result_digits(eagen_result* r, uint8_t* out);                     /* n x d (needs EAGEN_KEEP_DIGITS) */
+/* copy every function into one caller buffer: for k = 0..nf-1: a_k then b_k, tightly packed; returns bytes */
+int eagen_result_copy_all(eagen_result* r, uint64_t* out, size_t out_bytes, size_t* written);
+size_t eagen_result_total_bytes(const eagen_result* r);
+/* device time of the compute part of the call that produced this result (ms, CUDA events) */
+double eagen_result_device_ms(const eagen_result* r);
+void eagen_result_free(eagen_result* r);
+
+/* ---- helper API of regular_functions_utils ------------------------------------------------------------ */
+
+/* &Polynomial * &Polynomial                                   src/regular_functions_utils.rs:209-216
+ * out must hold la + lb - 1 elements (0 when both are empty).  Exact arithmetic: bits equal mul_naive/mul_fft. */
+int eagen_poly_mul(eagen_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* b, size_t lb, uint64_t* out);
+
+/* best_fft(a, omega_pow(S - log_n) or its inverse, log_n): natural order in and out, unscaled
+ *                                                             src/regular_functions_utils.rs:119-124        */
+int eagen_ntt(eagen_ctx* ctx, uint64_t* data, uint32_t log_n, int inverse);
+
+/* FftPrecomp::omega_pow / omega_pow_inv / half_pow            src/regular_functions_utils.rs:17-24
+ * (the Pasta tables the reference lacks: src/precomputed_fft_data.rs only covers bn256::Fr)                 */
+int eagen_fft_precomp(int curve, int which /*0 omega_pow, 1 omega_pow_inv, 2 half_pow*/, uint64_t exp, uint64_t* out);
+
+/* batched field inversion, in place (0 stays 0)               z.invert() at src/regular_functions_utils.rs:351-352 */
+int eagen_batch_invert(eagen_ctx* ctx, uint64_t* elems, size_t n);
+
+/* RegularFunction::ev at many points                          src/regular_functions_utils.rs:228-237
+ * pts: n Jacobian points; out: n field elements (0 for identity points)                                     */
+int eagen_eval_function(eagen_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* b, size_t lb,
+                        const uint64_t* pts, size_t n, uint64_t* out);
+
+/* ---- synthetic inputs (tests / bench.py) ------------------------------------------------
+ * n scalars uniform in [0, 2^127) (Montgomery, scalar field) and n distinct points (a + j*b)*G as Jacobian triples
+ * with non-trivial z, both functions of `seed` only.  Host-buffer and device-pointer variants.               */
+int eagen_synth_inputs(eagen_ctx* ctx, uint64_t seed, size_t n, uint64_t* scalars, uint64_t* pts);
+int eagen_dev_synth_inputs(eagen_ctx* ctx, uint64_t seed, size_t n, void* d_scalars, void* d_pts);
+
+/* ---- device-resident entry points (inputs/outputs are CUDA device pointers on the context's device) ------
+ * Used by bench.py (inputs already in HBM) and by the multi-GPU driver, which shards the point range across
+ * ranks, all-gathers the per-rank partial digit sums and assigns digit positions (trees) to ranks.
+ */
+/* stage A on a point shard: digits planes (d x n, u8), multiples table (n x (base-1) affine) and the d partial
+ * digit sums of this shard as homogeneous projective points (d x 96 B, X|Y|Z).                              */
+int eagen_dev_shard_sums(eagen_ctx* ctx, const void* d_scalars, const void* d_pts, size_t n, uint8_t base,
+                         void* d_planes, void* d_table, void* d_partial_sums);
+/* stage B: carry chain over `nparts` gathered partial sums (nparts x d projective) -> d affine carries      */
+int eagen_dev_carry_chain(eagen_ctx* ctx, const void* d_partial_sums, int nparts, uint8_t base, void* d_carries);
+/* stage C: divisor witnesses for the digit positions [pos_begin, pos_end) of the MSD-first iteration order,
+ * from the full planes / table of all n points.                                                             */
+int eagen_dev_trees(eagen_ctx* ctx, const void* d_planes, const void* d_table, const void* d_carries, size_t n,
+                    uint8_t base, uint32_t pos_begin, uint32_t pos_end, uint32_t flags, eagen_result** out);
+/* whole path with device-resident inputs */
+int eagen_dev_lhs_witness(eagen_ctx* ctx, const void* d_scalars, const void* d_pts, size_t n, uint8_t base,
+                          uint32_t flags, eagen_result** out);
+/* device pointers of a result's packed functions (layout: function k at a + k*a_stride elements ...) */
+int eagen_result_device_view(eagen_result* r, const void** d_a, size_t* a_stride, const void** d_b, size_t* b_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EAGEN_MSM_H */

