@@ -42,6 +42,7 @@ ABI_SYMBOLS = [
     "eagen_poly_mul", "eagen_ntt", "eagen_fft_precomp", "eagen_batch_invert", "eagen_eval_function",
     "eagen_dev_shard_sums", "eagen_dev_carry_chain", "eagen_dev_trees", "eagen_dev_lhs_witness",
     "eagen_result_device_view", "eagen_synth_inputs", "eagen_dev_synth_inputs",
+    "eagen_set_profiling", "eagen_profile_reset", "eagen_profile_json", "eagen_microbench",
 ]
 SELFTEST_SYMBOLS = ["eagen_selftest_field", "eagen_selftest_curve", "eagen_selftest_negbase_params", "eagen_selftest_ntt_plan"]
 
@@ -104,6 +105,10 @@ def lib():
         L.eagen_dev_trees.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8, C.c_uint32, C.c_uint32,
                                       C.c_uint32, C.POINTER(C.c_void_p)]
         L.eagen_result_device_view.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+        L.eagen_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        L.eagen_microbench.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.eagen_profile_reset.argtypes = [C.c_void_p]
+        L.eagen_profile_json.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         L.eagen_synth_inputs.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t, U64P, U64P]
         L.eagen_dev_synth_inputs.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t, C.c_void_p, C.c_void_p]
         L.eagen_selftest_field.argtypes = [C.c_int, C.c_int, U64P, U64P, U64P]
@@ -254,6 +259,24 @@ class Context:
 
     def launch_count(self):
         return lib().eagen_launch_count(self._h)
+
+    def microbench(self, which):
+        v = C.c_double()
+        self._chk(lib().eagen_microbench(self._h, which, C.byref(v)))
+        return v.value
+
+    def set_profiling(self, on=True):
+        self._chk(lib().eagen_set_profiling(self._h, int(on)))
+
+    def profile_reset(self):
+        self._chk(lib().eagen_profile_reset(self._h))
+
+    def profile(self):
+        """list of dicts: kernel group, launches, ms (CUDA events), algorithmic bytes and modmul counts"""
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        self._chk(lib().eagen_profile_json(self._h, buf, len(buf)))
+        return json.loads(buf.value.decode())
 
     # ---- the path ----------------------------------------------------------------------------------------
     def negbase_decompose(self, scalars, base):

@@ -102,6 +102,28 @@ void eagen_ctx_destroy(eagen_ctx* ctx) {
 const char* eagen_last_error(const eagen_ctx* ctx) { return ctx ? ctx->err.c_str() : g_global_err.c_str(); }
 uint64_t eagen_launch_count(const eagen_ctx* ctx) { return ctx ? ctx->eng->launches() : 0; }
 
+int eagen_microbench(eagen_ctx* ctx, int which, double* ops_per_second) {
+    if (!ctx || !ops_per_second || which < 0 || which > 1) return EAGEN_E_ARG;
+    return guarded(ctx, [&] { *ops_per_second = ctx->eng->microbench(which); });
+}
+int eagen_set_profiling(eagen_ctx* ctx, int on) {
+    if (!ctx) return EAGEN_E_ARG;
+    ctx->eng->set_profiling(on != 0);
+    return EAGEN_OK;
+}
+int eagen_profile_reset(eagen_ctx* ctx) {
+    if (!ctx) return EAGEN_E_ARG;
+    ctx->eng->profile_reset();
+    return EAGEN_OK;
+}
+int eagen_profile_json(eagen_ctx* ctx, char* buf, size_t cap) {
+    if (!ctx || !buf || cap == 0) return EAGEN_E_ARG;
+    std::string j = ctx->eng->profile_json();
+    if (j.size() + 1 > cap) return EAGEN_E_LEN;
+    std::memcpy(buf, j.c_str(), j.size() + 1);
+    return EAGEN_OK;
+}
+
 int eagen_num_digits(int curve, uint8_t base, uint32_t* d) {
     return guarded(nullptr, [&] { need(d && base >= 2, "eagen_num_digits: null output or base < 2"); *d = digits_of_curve(curve, base); });
 }

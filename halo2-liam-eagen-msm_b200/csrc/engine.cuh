@@ -87,6 +87,10 @@ struct IEngine {
     virtual void eval_host(const uint64_t* a, size_t la, const uint64_t* b, size_t lb, const uint64_t* pts, size_t n, uint64_t* out) = 0;
     virtual void shard_sums_dev(const void* d_scalars, const void* d_pts, size_t n, uint8_t base, void* d_planes, void* d_table, void* d_sums) = 0;
     virtual void carry_chain_dev(const void* d_sums, int nparts, uint8_t base, void* d_carries) = 0;
+    virtual double microbench(int which) = 0;
+    virtual void set_profiling(bool on) = 0;
+    virtual std::string profile_json() = 0;
+    virtual void profile_reset() = 0;
     virtual void synth_dev(uint64_t seed, size_t n, void* d_scalars, void* d_pts) = 0;
     virtual void synth_host(uint64_t seed, size_t n, uint64_t* scalars, uint64_t* pts) = 0;
     virtual ResultImpl* trees_dev(const void* d_planes, const void* d_table, const void* d_carries, size_t n, uint8_t base,
@@ -205,6 +209,23 @@ public:
     int device() const override { return dev_; }
     uint64_t launches() const override { return launches_; }
 
+    // ---- per-kernel-group profiling: CUDA events on the launching stream + exact work counts from launch parameters
+    void set_profiling(bool on) override { prof_on_ = on; }
+    void profile_reset() override { for (auto& e : prof_) { e.launches = 0; e.scopes = 0; e.ms = 0; e.bytes = 0; e.modmul = 0; } }
+    std::string profile_json() override {
+        prof_collect();
+        std::string o = "[";
+        bool first = true;
+        for (auto& e : prof_) {
+            if (!e.scopes) continue;
+            char buf[512];
+            snprintf(buf, sizeof buf, "%s{\"kernel\": \"%s\", \"launches\": %llu, \"scopes\": %llu, \"ms\": %.6f, \"bytes\": %.0f, \"modmul\": %.0f}",
+                     first ? "" : ", ", e.name.c_str(), (unsigned long long)e.launches, (unsigned long long)e.scopes, e.ms, e.bytes, e.modmul);
+            o += buf; first = false;
+        }
+        return o + "]";
+    }
+
     // ------------------------------------------------------------------------------------------------
     // public operations
     // ------------------------------------------------------------------------------------------------
@@ -299,6 +320,30 @@ public:
         float ms = 0; EAGEN_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
         res->device_ms = ms;
         return res.release();
+    }
+
+    // which = 0: 32-bit IMAD per second; which = 1: base-field Montgomery products per second (register-resident chains)
+    double microbench(int which) override {
+        use();
+        int sms = 0;
+        EAGEN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev_));
+        const int blocks = sms * 8, threads = 256;
+        void* buf = den_.ensure((size_t)blocks * threads * 32);
+        double best = 0;
+        for (int rep = 0; rep < 4; ++rep) {
+            const int iters = which == 0 ? 4096 : 512;
+            EAGEN_CUDA(cudaEventRecord(ev0_, st_));
+            if (which == 0) k_imad_peak<<<blocks, threads, 0, st_>>>((uint32_t*)buf, iters, 12345u + rep);
+            else k_modmul_peak<FB><<<blocks, threads, 0, st_>>>((F*)buf, iters);
+            ++launches_;
+            EAGEN_CUDA(cudaGetLastError());
+            EAGEN_CUDA(cudaEventRecord(ev1_, st_));
+            EAGEN_CUDA(cudaStreamSynchronize(st_));
+            float ms = 0; EAGEN_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+            double ops = (double)blocks * threads * (double)iters * (which == 0 ? 128.0 : 4.0);
+            best = std::max(best, ops / (ms * 1e-3));
+        }
+        return best;
     }
 
     void synth_dev(uint64_t seed, size_t n, void* d_scalars, void* d_pts) override {
@@ -430,6 +475,53 @@ public:
     }
 
 private:
+    struct ProfEntry { std::string name; uint64_t launches = 0, scopes = 0; double ms = 0, bytes = 0, modmul = 0; };
+    struct ProfPending { int tag; cudaEvent_t a, b; uint64_t l0, l1; };
+    bool prof_on_ = false;
+    std::vector<ProfEntry> prof_;
+    std::vector<ProfPending> pending_;
+    std::vector<cudaEvent_t> evpool_;
+    int prof_tag(const char* name) {
+        for (size_t i = 0; i < prof_.size(); ++i) if (prof_[i].name == name) return (int)i;
+        ProfEntry e; e.name = name; prof_.push_back(e);
+        return (int)prof_.size() - 1;
+    }
+    cudaEvent_t get_event() {
+        if (!evpool_.empty()) { cudaEvent_t e = evpool_.back(); evpool_.pop_back(); return e; }
+        cudaEvent_t e; EAGEN_CUDA(cudaEventCreate(&e)); return e;
+    }
+    // RAII scope: events around the launches issued while it is alive
+    struct Scope {
+        Engine* eng; bool live;
+        Scope(Engine* e, const char* name, double bytes, double modmul) : eng(e), live(e->prof_on_) {
+            if (!live) return;
+            int tag = eng->prof_tag(name);
+            eng->prof_[tag].bytes += bytes; eng->prof_[tag].modmul += modmul; eng->prof_[tag].scopes += 1;
+            ProfPending p; p.tag = tag; p.a = eng->get_event(); p.b = eng->get_event(); p.l0 = eng->launches_; p.l1 = 0;
+            cudaEventRecord(p.a, eng->st_);
+            eng->pending_.push_back(p);
+            idx = eng->pending_.size() - 1;
+        }
+        ~Scope() {
+            if (!live) return;
+            ProfPending& p = eng->pending_[idx];
+            cudaEventRecord(p.b, eng->st_);
+            p.l1 = eng->launches_;
+        }
+        size_t idx = 0;
+    };
+    void prof_collect() {
+        if (pending_.empty()) return;
+        cudaStreamSynchronize(st_);
+        for (auto& p : pending_) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) prof_[p.tag].ms += ms;
+            prof_[p.tag].launches += p.l1 - p.l0;
+            evpool_.push_back(p.a); evpool_.push_back(p.b);
+        }
+        pending_.clear();
+    }
+
     int dev_;
     cudaStream_t st_ = nullptr;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
@@ -440,6 +532,7 @@ private:
     DevBuf tw_fwd_, tw_inv_;
     DevBuf in_scalars_, in_points_, planes_, rows_, table_, sums_, partials_, carries_, carries_proj_;
     DevBuf cnt_, tree_n_, tree_of_pos_, tpts_;
+    std::unique_ptr<Scope> prof_scope_;
     DevBuf ptlev_, lvlcnt_, a_[2], b_[2], ea_, eb_, oa_, ob_, den_, binv_, desc_, tops_, lead_;
 
     void use() { EAGEN_CUDA(cudaSetDevice(dev_)); }
@@ -462,6 +555,7 @@ private:
 
     void sync_check() {
         EAGEN_CUDA(cudaStreamSynchronize(st_));
+        prof_collect();
         int e = 0;
         EAGEN_CUDA(cudaMemcpy(&e, d_err_, sizeof(int), cudaMemcpyDeviceToHost));
         if (e) {
@@ -493,6 +587,7 @@ private:
     // in-place batched inversion of M elements (zeros stay zero)
     void batch_invert(F* x, size_t M) {
         if (M == 0) return;
+        Scope ps(this, "batch_invert", 160.0 * M * (1.0 + 1.0 / (BINV_G - 1)), 3.0 * M * (1.0 + 1.0 / (BINV_G - 1)));
         // level sizes
         std::vector<size_t> sz{M};
         while (sz.back() > 1024) sz.push_back((sz.back() + BINV_G - 1) / BINV_G);
@@ -511,7 +606,17 @@ private:
 
     // batched transform of n_tr arrays of size 2^t living in `data`; optional compact gather / scatter
     void ntt(bool inverse, F* data, const F* src, size_t src_stride, int src_len, F* dst, size_t dst_stride, int dst_len,
-             int t, size_t n_tr, const int* counts, int node_max) {
+             int t, size_t n_tr, const int* counts, int node_max, size_t n_present = (size_t)-1) {
+        if (n_present == (size_t)-1) n_present = n_tr;
+        {   // algorithmic work: every present element is read and written once per pass, t/2 modmul per element in total
+            std::vector<std::pair<int, int>> pl = ntt_plan(t);
+            double el = (double)n_present * (double)((size_t)1 << t);
+            double bytes = 64.0 * el * pl.size();
+            if (src) bytes -= 32.0 * el - 32.0 * (double)n_present * src_len;
+            if (dst) bytes -= 32.0 * el - 32.0 * (double)n_present * dst_len;
+            prof_scope_.reset(new Scope(this, inverse ? "ntt_inverse" : "ntt_forward", bytes, el * t / 2.0));
+        }
+        struct Closer { std::unique_ptr<Scope>& s; ~Closer() { s.reset(); } } closer{prof_scope_};
         NttPass<FB> a;
         a.data = data; a.tw = tw(inverse, t); a.counts = counts; a.node_max = node_max;
         a.total = n_tr << t; a.t = t;
@@ -531,6 +636,7 @@ private:
     }
 
     void run_negbase(const Fe<FS>* ds, size_t n, const NegbaseParams& prm, uint8_t* planes, uint8_t* rows) {
+        Scope ps(this, "negbase", (double)n * (32.0 + prm.d * (rows ? 2.0 : 1.0)), (double)n);
         launch(k_negbase<FS>, n, 128, ds, n, prm, planes, rows, d_err_);
     }
 
@@ -538,8 +644,12 @@ private:
         size_t m = n * (size_t)(base - 1);
         if (m == 0) return;
         F* zs = (F*)den_.ensure(m * 32);
-        launch(k_multiples_proj<CC>, n, 128, dp, n, (uint32_t)base, tab, zs);
+        {
+            Scope ps(this, "multiples", (double)n * 96.0 + (double)m * 96.0, (double)n * (3.0 + 14.0 * (base - 2)));
+            launch(k_multiples_proj<CC>, n, 128, dp, n, (uint32_t)base, tab, zs);
+        }
         batch_invert(zs, m);
+        Scope ps(this, "multiples_finish", (double)m * 160.0, (double)m * 2.0);
         launch(k_scale_by_zinv<FB>, m, 256, tab, (const F*)zs, m);
     }
 
@@ -553,6 +663,8 @@ private:
         size_t chunk = (size_t)SUMS_THREADS * per_thread;
         int chunks = (int)std::max<size_t>(1, (n + chunk - 1) / chunk);
         Prj* partials = (Prj*)partials_.ensure((size_t)d * chunks * sizeof(Prj));
+        // work: one table point (64 B) + one digit per (position, point) with a non-zero digit (~(b-1)/b of them), 13 modmul per mixed add
+        Scope ps(this, "digit_sums", (double)n * d * (1.0 + 64.0 * (prm.base - 1) / prm.base), (double)n * d * 13.0 * (prm.base - 1) / prm.base);
         launch2d(k_digit_sums<CC>, dim3(chunks, d), SUMS_THREADS, (const uint8_t*)planes, (const Aff*)tab, n, prm.base, per_thread, partials);
         launch2d(k_reduce_partials<CC>, dim3(d, 1), SUMS_THREADS, (const Prj*)partials, chunks, sums);
     }
@@ -560,6 +672,7 @@ private:
     void run_carry_chain(const Prj* sums, int nparts, uint32_t d, uint8_t base, Aff* carries) {
         Prj* cp = (Prj*)carries_proj_.ensure((size_t)d * sizeof(Prj));
         F* zs = (F*)lead_.ensure((size_t)d * 32);
+        Scope ps(this, "carry_chain", (double)d * 96.0 * (nparts + 1), (double)d * (14.0 * nparts + 14.0 * 4));
         launch(k_carry_chain<CC>, 1, 32, sums, d, (uint32_t)base, nparts, cp, zs);
         batch_invert(zs, d);
         launch(k_proj_to_affine<FB>, d, 64, (const Prj*)cp, (const F*)zs, (size_t)d, carries);
@@ -573,8 +686,11 @@ private:
         int chunks = (int)std::max<size_t>(1, (n + CHUNK_PTS - 1) / CHUNK_PTS);
         int* cnt = (int*)cnt_.ensure((size_t)d * chunks * sizeof(int));
         int* tree_n = (int*)tree_n_.ensure((size_t)d * sizeof(int));
-        launch2d(k_count_nonzero, dim3(chunks, d), 256, planes, n, chunks, cnt);
-        launch(k_scan_chunks<FB>, d, 64, cnt, chunks, d, (uint32_t)base, carries, tree_n);
+        {
+            Scope ps(this, "count_scan", (double)n * d, 0.0);
+            launch2d(k_count_nonzero, dim3(chunks, d), 256, planes, n, chunks, cnt);
+            launch(k_scan_chunks<FB>, d, 64, cnt, chunks, d, (uint32_t)base, carries, tree_n);
+        }
         std::vector<int> hn(d);
         EAGEN_CUDA(cudaMemcpyAsync(hn.data(), tree_n, (size_t)d * sizeof(int), cudaMemcpyDeviceToHost, st_));
         EAGEN_CUDA(cudaStreamSynchronize(st_));
@@ -603,8 +719,11 @@ private:
             EAGEN_CUDA(cudaMemcpyAsync(tree_of_pos, map.data(), (size_t)d * sizeof(int), cudaMemcpyHostToDevice, st_));
             EAGEN_CUDA(cudaStreamSynchronize(st_));  // `map` is a stack temporary
             Aff* T = (Aff*)tpts_.ensure((size_t)nt * nmax * sizeof(Aff));
-            launch2d(k_scatter_points<FB>, dim3(chunks, d), 256, planes, tab, n, (uint32_t)base, (const int*)cnt, chunks, carries,
-                     (const int*)tree_n, (const int*)tree_of_pos, T, nmax);
+            {
+                Scope ps(this, "scatter_points", (double)nt * ((double)n + 128.0 * (double)nmax), 0.0);
+                launch2d(k_scatter_points<FB>, dim3(chunks, d), 256, planes, tab, n, (uint32_t)base, (const int*)cnt, chunks, carries,
+                         (const int*)tree_n, (const int*)tree_of_pos, T, nmax);
+            }
             // result slot of position p is k = d-1-p; within this result handle slots are relative to the range:
             // slot = (pos_end-1-p), so slot 0 is the highest position of the range (= lowest k)
             run_trees(T, nmax, cnts, flags, res, /*first slot*/ pos_end - g1, /*reverse*/ -1, roots.data() + (g0 - pos_begin));
@@ -678,12 +797,22 @@ private:
         MergeDesc<FB>* desc = (MergeDesc<FB>*)desc_.ensure(std::max<size_t>((size_t)nt * (L ? node_max[1] : 1), 1) * sizeof(MergeDesc<FB>));
         if (L) ensure_twiddles(L);
 
+        // present nodes per level (exact work counts for the profiler)
+        std::vector<double> present(L + 1, 0.0);
+        for (int l = 0; l <= L; ++l) for (int tr = 0; tr < nt; ++tr) present[l] += lv[(size_t)(l + 1) * nt + tr];
+
         // level 0: outputs -(P+Q) and the line functions
         size_t w0 = (size_t)nt * node_max[0];
-        launch(k_pair_den<FB>, w0, 256, T, cap, (const int*)dlv, node_max[0], nt, den);
+        {
+            Scope ps(this, "pair_points", present[0] * (128.0 + 32.0), 0.0);
+            launch(k_pair_den<FB>, w0, 256, T, cap, (const int*)dlv, node_max[0], nt, den);
+        }
         batch_invert(den, w0);
-        launch(k_pair_finish<FB>, w0, 256, T, cap, (const int*)dlv, node_max[0], nt, (const F*)den, 1, PT + pt_off[0]);
-        launch(k_leaf_lines<FB>, w0, 256, T, cap, (const int*)dlv, (const Aff*)(PT + pt_off[0]), node_max[0], nt, A[0], B[0]);
+        {
+            Scope ps(this, "pair_points", present[0] * (128.0 + 32.0 + 64.0 + 128.0 + 64.0 + 96.0), present[0] * (4.0 + 2.0));
+            launch(k_pair_finish<FB>, w0, 256, T, cap, (const int*)dlv, node_max[0], nt, (const F*)den, 1, PT + pt_off[0]);
+            launch(k_leaf_lines<FB>, w0, 256, T, cap, (const int*)dlv, (const Aff*)(PT + pt_off[0]), node_max[0], nt, A[0], B[0]);
+        }
 
         int cur = 0;
         for (int l = 0; l < L; ++l) {
@@ -691,32 +820,50 @@ private:
             const size_t m = (size_t)1 << l, Tn = 2 * m;
             const size_t nodes = node_max[l], merges = node_max[l + 1];
             const size_t wm = (size_t)nt * merges;
+            const double pts = present[l + 1] * (double)Tn;  // evaluation points of this level
             Aff* Pc = PT + pt_off[l];
             Aff* Pp = PT + pt_off[l + 1];
             // output points of the parents and the merge descriptors
-            launch(k_pair_den<FB>, wm, 256, (const Aff*)Pc, nodes, cnt_of(l), merges, nt, den);
+            {
+                Scope ps(this, "pair_points", present[l + 1] * (128.0 + 32.0), 0.0);
+                launch(k_pair_den<FB>, wm, 256, (const Aff*)Pc, nodes, cnt_of(l), merges, nt, den);
+            }
             batch_invert(den, wm);
-            launch(k_pair_finish<FB>, wm, 256, (const Aff*)Pc, nodes, cnt_of(l), merges, nt, (const F*)den, 0, Pp);
             F tinv = half_pow(t);
-            launch(k_merge_desc<FB>, wm, 128, (const Aff*)Pc, nodes, cnt_of(l), (const Aff*)Pp, merges, nt, tinv, desc);
+            {
+                Scope ps(this, "pair_points", present[l + 1] * (128.0 + 32.0 + 64.0 + 192.0 + 272.0), present[l + 1] * (4.0 + 5.0));
+                launch(k_pair_finish<FB>, wm, 256, (const Aff*)Pc, nodes, cnt_of(l), merges, nt, (const F*)den, 0, Pp);
+                launch(k_merge_desc<FB>, wm, 128, (const Aff*)Pc, nodes, cnt_of(l), (const Aff*)Pp, merges, nt, tinv, desc);
+            }
             // children -> evaluation domain
-            ntt(false, EA, A[cur], m + 1, (int)(m + 1), nullptr, 0, 0, t, (size_t)nt * nodes, cnt_of(l), (int)nodes);
-            ntt(false, EB, B[cur], m, (int)m, nullptr, 0, 0, t, (size_t)nt * nodes, cnt_of(l), (int)nodes);
+            ntt(false, EA, A[cur], m + 1, (int)(m + 1), nullptr, 0, 0, t, (size_t)nt * nodes, cnt_of(l), (int)nodes, (size_t)present[l]);
+            ntt(false, EB, B[cur], m, (int)m, nullptr, 0, 0, t, (size_t)nt * nodes, cnt_of(l), (int)nodes, (size_t)present[l]);
             // pointwise merge with exact division
-            launch(k_den<FB>, wm << t, 256, (const MergeDesc<FB>*)desc, wm, t, tw(false, t), den, d_err_);
+            {
+                Scope ps(this, "merge_den", pts * 32.0, pts * 1.0);
+                launch(k_den<FB>, wm << t, 256, (const MergeDesc<FB>*)desc, wm, t, tw(false, t), den, d_err_);
+            }
             batch_invert(den, wm << t);
-            launch(k_pointwise<CC>, wm << t, 128, (const MergeDesc<FB>*)desc, wm, t, tw(false, t), tinv, (const F*)EA, (const F*)EB,
-                   (const F*)den, merges, nodes, OA, OB);
+            {
+                Scope ps(this, "merge_pointwise", pts * 224.0, pts * 15.0);
+                launch(k_pointwise<CC>, wm << t, 128, (const MergeDesc<FB>*)desc, wm, t, tw(false, t), tinv, (const F*)EA, (const F*)EB,
+                       (const F*)den, merges, nodes, OA, OB);
+            }
             // back to coefficients, compact parent slots
-            ntt(true, OA, nullptr, 0, 0, A[cur ^ 1], Tn + 1, (int)Tn, t, wm, cnt_of(l + 1), (int)merges);
-            ntt(true, OB, nullptr, 0, 0, B[cur ^ 1], Tn, (int)Tn, t, wm, cnt_of(l + 1), (int)merges);
-            launch(k_fixup<FB>, wm, 128, (const MergeDesc<FB>*)desc, wm, t, merges, nodes, (const F*)A[cur], (const F*)B[cur], A[cur ^ 1]);
+            ntt(true, OA, nullptr, 0, 0, A[cur ^ 1], Tn + 1, (int)Tn, t, wm, cnt_of(l + 1), (int)merges, (size_t)present[l + 1]);
+            ntt(true, OB, nullptr, 0, 0, B[cur ^ 1], Tn, (int)Tn, t, wm, cnt_of(l + 1), (int)merges, (size_t)present[l + 1]);
+            {
+                Scope ps(this, "merge_fixup", present[l + 1] * (6 * 32.0 + 64.0), present[l + 1] * 5.0);
+                launch(k_fixup<FB>, wm, 128, (const MergeDesc<FB>*)desc, wm, t, merges, nodes, (const F*)A[cur], (const F*)B[cur], A[cur ^ 1]);
+            }
             cur ^= 1;
         }
         // roots: one node per tree at level L (node_max[L] == 1)
         const size_t ra = ((size_t)1 << L) + 1, rb = (size_t)1 << L;
         int* tops = (int*)tops_.ensure((size_t)2 * nt * sizeof(int));
         EAGEN_CUDA(cudaMemsetAsync(tops, 0, (size_t)2 * nt * sizeof(int), st_));
+        Scope ps_can(this, "canonical_form", (double)nt * (double)(ra + rb) * 32.0 * ((flags & EAGEN_RAW_TREE) ? 1.0 : 3.0),
+                     (flags & EAGEN_RAW_TREE) ? 0.0 : (double)nt * (double)(ra + rb));
         launch2d(k_find_top<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, (const F*)A[cur], ra, (int)ra, tops);
         launch2d(k_find_top<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, (const F*)B[cur], rb, (int)rb, tops + nt);
         if (!(flags & EAGEN_RAW_TREE)) {

@@ -808,6 +808,7 @@ __global__ void k_eval_function(const Fe<FP>* __restrict__ A, int la, const Fe<F
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     Affine<FP> p = ldg_aff(pts + j);
+    if (p.is_identity()) { stg(out + j, Fe<FP>::zero()); return; }
     Fe<FP> va = Fe<FP>::zero(), vb = Fe<FP>::zero();
     for (int i = la - 1; i >= 0; --i) va = add(mul(va, p.x), ldg(A + i));
     for (int i = lb - 1; i >= 0; --i) vb = add(mul(vb, p.x), ldg(B + i));
@@ -855,6 +856,43 @@ __global__ void k_synth_inputs(uint64_t seed, size_t n, Fe<typename CC::Scalar>*
     stg(jac + 3 * j, mul(acc.x, acc.z));
     stg(jac + 3 * j + 1, mul(acc.y, zz));
     stg(jac + 3 * j + 2, acc.z);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Integer-pipe micro-benchmarks: the roofline denominators MEASURED_PEAKS.json does not carry.
+//   k_imad_peak   : 16 independent 32-bit IMAD chains per thread, no memory traffic  -> IMAD/s of the chip
+//   k_modmul_peak : 4 independent Montgomery-product chains per thread               -> modmul/s ceiling of mul()
+// ------------------------------------------------------------------------------------------------
+static __global__ void k_imad_peak(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed + threadIdx.x * 16 + i;
+    uint32_t m = seed | 1, c = blockIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = a[i] * m + c;
+        }
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x ^= a[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+template <class FP>
+__global__ void k_modmul_peak(Fe<FP>* out, int iters) {
+    Fe<FP> a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { a[i] = Fe<FP>::one(); a[i].v[0] += threadIdx.x * 4 + i; a[i].v[1] = blockIdx.x; }
+    Fe<FP> m = Fe<FP>::r2();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = mul(a[i], m);
+    }
+    Fe<FP> x = add(add(a[0], a[1]), add(a[2], a[3]));
+    stg(out + (size_t)blockIdx.x * blockDim.x + threadIdx.x, x);
 }
 
 }  // namespace eagen

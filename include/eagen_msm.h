@@ -71,6 +71,15 @@ const char* eagen_status_string(int status);
 /* number of kernels this context has launched so far (bench.py reports the per-step delta as gpu_launches) */
 uint64_t eagen_launch_count(const eagen_ctx* ctx);
 
+/* per-kernel-group profiling (CUDA events on the launching stream + exact byte / modmul counts from the launch
+ * parameters).  eagen_profile_json writes a JSON array [{"kernel", "launches", "scopes", "ms", "bytes", "modmul"}, ...]. */
+int eagen_set_profiling(eagen_ctx* ctx, int on);
+/* integer-pipe roofline denominators measured on this device: which = 0 -> dependent-free 32-bit IMAD per second,
+ * which = 1 -> base-field Montgomery products per second in a register-resident loop (ceiling of the field code) */
+int eagen_microbench(eagen_ctx* ctx, int which, double* ops_per_second);
+int eagen_profile_reset(eagen_ctx* ctx);
+int eagen_profile_json(eagen_ctx* ctx, char* buf, size_t cap);
+
 /* ---- host-side scalars of the path ---------------------------------------------------------------------
  * order / isqrt / logb_ceil: d = logb_ceil(isqrt(order)+2, base) + 1      src/argument_witness_calc.rs:32-40,54-56,89-91 */
 int eagen_num_digits(int curve, uint8_t base, uint32_t* d);

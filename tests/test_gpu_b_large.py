@@ -53,7 +53,7 @@ def test_config2_sampled_trees_vs_oracle(gpu_ctx, oracle, eagen, cname, log_n):
     mult = ctx.precompute_multiplicities(P, base)
     one = oracle.pack_felts([1], cv.p)[0]
     d = ro.d
-    for i in (0, 17, d - 1):
+    for i in (1, 17, d - 1):
         rows, _ = build_tmp(mult, ro.digits, ro.carries, i, base)
         parts = []
         if i and ro.carries[i - 1].any():
@@ -82,7 +82,7 @@ def test_config3_2pow20_properties(gpu_ctx, oracle, eagen):
     # per-position structure: degrees and vanishing on sampled points of tmp_i
     mult = ctx.precompute_multiplicities(P, base)
     one = oracle.pack_felts([1], cv.p)[0]
-    for i in (0, 29, d - 1):
+    for i in (2, 29, d - 1):  # position 0 is empty for scalars < 2^127 (5^55 > 2^127): f = 1 there
         rows, idx = build_tmp(mult, digits, carries, i, base)
         extra = (base if (i and carries[i - 1].any()) else 0) + (1 if carries[i].any() else 0)
         npts = len(rows) + extra
@@ -95,5 +95,7 @@ def test_config3_2pow20_properties(gpu_ctx, oracle, eagen):
         vals = ctx.eval_function(f, affine_to_jac(np.concatenate(pts), one))
         assert not vals.any()
         # the function must NOT vanish on an unrelated point
-        other = ctx.eval_function(f, P[:4])
+        other = ctx.eval_function(f, ctx.synth_inputs(0x0BADC0DE, 4)[1])
         assert other.any(axis=1).all()
+    f0 = res.function(d - 1)  # iteration 0: tmp = [-carry] = [O]  ->  the constant 1
+    assert len(f0.a) == 1 and len(f0.b) == 0 and (f0.a[0] == one).all()
