@@ -319,6 +319,7 @@ template <class FP> void st_field(int op, const uint64_t* a, const uint64_t* b, 
         case 3: r = inv(x); break;
         case 4: r = from_canonical(x); break;
         case 5: r = to_canonical(x); break;
+        case 6: r = mul_chain(x, y); break;  // the device algorithm with a host-emulated carry flag
         default: throw StatusError{EAGEN_E_ARG, "bad op"};
     }
     std::memcpy(out, r.v, 32);

@@ -152,9 +152,9 @@ EAGEN_HD Fe<FP> neg(const Fe<FP>& a) { return sub(Fe<FP>::zero(), a); }
 template <class FP>
 EAGEN_HD Fe<FP> dbl(const Fe<FP>& a) { return add(a, a); }
 
-// Montgomery product, CIOS over 32-bit limbs.
+// Portable Montgomery product, CIOS over 32-bit limbs with 64-bit temporaries (host path; reference for the PTX path).
 template <class FP>
-EAGEN_HD Fe<FP> mul(const Fe<FP>& a, const Fe<FP>& b) {
+EAGEN_HD Fe<FP> mul_portable(const Fe<FP>& a, const Fe<FP>& b) {
     uint32_t t[8];
     uint32_t t8 = 0;
 #pragma unroll
@@ -189,6 +189,143 @@ EAGEN_HD Fe<FP> mul(const Fe<FP>& a, const Fe<FP>& b) {
     for (int i = 0; i < 8; ++i) r.v[i] = t[i];
     reduce_once<FP>(r.v, t8);
     return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Carry-chain primitives.  Device: PTX mad.lo.cc / madc.hi.cc pairs, which ptxas fuses into IMAD.WIDE.U32(.X)
+// with the carry in a predicate, so a 32x32+64 multiply-accumulate with carry costs one issue slot.
+// Host: the same operations with an explicit carry flag, so the algorithm below can be tested on the CPU.
+// ------------------------------------------------------------------------------------------------
+namespace cc {
+#if defined(__CUDA_ARCH__)
+EAGEN_D void mul_lo(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+EAGEN_D void mul_hi(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+EAGEN_D void mad_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
+EAGEN_D void madc_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
+EAGEN_D void madc_hi_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
+EAGEN_D void madc_hi(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
+EAGEN_D void add_cc(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+EAGEN_D void addc_cc(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+EAGEN_D void addc(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("addc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+EAGEN_D void sub_cc(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+EAGEN_D void subc_cc(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+EAGEN_D void subc(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("subc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
+#else
+static thread_local uint32_t CF = 0;  // host emulation of the condition-code carry / borrow flag
+inline void mul_lo(uint32_t& d, uint32_t a, uint32_t b) { d = a * b; }
+inline void mul_hi(uint32_t& d, uint32_t a, uint32_t b) { d = (uint32_t)(((uint64_t)a * b) >> 32); }
+inline void mad_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)(a * b) + c; d = (uint32_t)t; CF = (uint32_t)(t >> 32); }
+inline void madc_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)(a * b) + c + CF; d = (uint32_t)t; CF = (uint32_t)(t >> 32); }
+inline void madc_hi_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c + CF; d = (uint32_t)t; CF = (uint32_t)(t >> 32); }
+inline void madc_hi(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c + CF; d = (uint32_t)t; }
+inline void add_cc(uint32_t& d, uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; d = (uint32_t)t; CF = (uint32_t)(t >> 32); }
+inline void addc_cc(uint32_t& d, uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + CF; d = (uint32_t)t; CF = (uint32_t)(t >> 32); }
+inline void addc(uint32_t& d, uint32_t a, uint32_t b) { d = a + b + CF; }
+inline void sub_cc(uint32_t& d, uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; d = (uint32_t)t; CF = (uint32_t)((t >> 32) & 1); }
+inline void subc_cc(uint32_t& d, uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - CF; d = (uint32_t)t; CF = (uint32_t)((t >> 32) & 1); }
+inline void subc(uint32_t& d, uint32_t a, uint32_t b) { d = a - b - CF; }
+#endif
+}  // namespace cc
+
+// One row of the interleaved (CIOS) Montgomery product on split accumulators.
+// The running sum is T = E + O*2^32 with E[0] == 0 on entry (E "even role": limb k = column k; O "odd role": limb k = column k+1).
+// The row computes T' = T/2^32 + a*bi + m*p with column 0 cleared; on exit the roles are swapped: O holds the even role
+// (O[0] == 0) and E the odd role.  Writing the new odd-role limb k from the old E[k+2] performs the shift for free.
+template <class FP, bool FIRST>
+EAGEN_HD void mont_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi) {
+    if (FIRST) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            cc::mul_lo(E[j], a[j + 1], bi); cc::mul_hi(E[j + 1], a[j + 1], bi);
+            cc::mul_lo(O[j], a[j], bi); cc::mul_hi(O[j + 1], a[j], bi);
+        }
+    } else {
+        cc::add_cc(O[0], O[0], E[1]);
+#pragma unroll
+        for (int j = 0; j < 6; j += 2) {
+            cc::madc_lo_cc(E[j], a[j + 1], bi, E[j + 2]);
+            cc::madc_hi_cc(E[j + 1], a[j + 1], bi, E[j + 3]);
+        }
+        cc::madc_lo_cc(E[6], a[7], bi, 0);
+        cc::madc_hi(E[7], a[7], bi, 0);
+        cc::mad_lo_cc(O[0], a[0], bi, O[0]);
+        cc::madc_hi_cc(O[1], a[0], bi, O[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            cc::madc_lo_cc(O[j], a[j], bi, O[j]);
+            cc::madc_hi_cc(O[j + 1], a[j], bi, O[j + 1]);
+        }
+        cc::addc(E[7], E[7], 0);
+    }
+    uint32_t m = O[0] * FP::INV;
+    // odd limbs of p onto the odd-role array; zero limbs only propagate the carry
+    bool started = false;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        if (FP::mod(j + 1) != 0) {
+            if (!started) cc::mad_lo_cc(E[j], FP::mod(j + 1), m, E[j]); else cc::madc_lo_cc(E[j], FP::mod(j + 1), m, E[j]);
+            if (j == 6) cc::madc_hi(E[j + 1], FP::mod(j + 1), m, E[j + 1]); else cc::madc_hi_cc(E[j + 1], FP::mod(j + 1), m, E[j + 1]);
+            started = true;
+        } else if (started) {
+            cc::addc_cc(E[j], E[j], 0);
+            if (j == 6) cc::addc(E[j + 1], E[j + 1], 0); else cc::addc_cc(E[j + 1], E[j + 1], 0);
+        }
+    }
+    // even limbs of p onto the even-role array (p[0] is odd, hence never zero); the carry out lands in column 8 = E[7]
+    cc::mad_lo_cc(O[0], FP::mod(0), m, O[0]);
+    cc::madc_hi_cc(O[1], FP::mod(0), m, O[1]);
+#pragma unroll
+    for (int j = 2; j < 8; j += 2) {
+        if (FP::mod(j) != 0) {
+            cc::madc_lo_cc(O[j], FP::mod(j), m, O[j]);
+            cc::madc_hi_cc(O[j + 1], FP::mod(j), m, O[j + 1]);
+        } else {
+            cc::addc_cc(O[j], O[j], 0);
+            cc::addc_cc(O[j + 1], O[j + 1], 0);
+        }
+    }
+    cc::addc(E[7], E[7], 0);
+}
+
+// final a < 2p -> [0, p) with a borrow chain and selects
+template <class FP>
+EAGEN_HD void reduce_once_cc(uint32_t* r) {
+    uint32_t s[8], brw;
+    cc::sub_cc(s[0], r[0], FP::mod(0));
+#pragma unroll
+    for (int i = 1; i < 8; ++i) cc::subc_cc(s[i], r[i], FP::mod(i));
+    cc::subc(brw, 0, 0);  // 0 - 0 - borrow: all ones when r < p
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = brw ? r[i] : s[i];
+}
+
+// Montgomery product on carry chains (device fast path; host-emulated for tests)
+template <class FP>
+EAGEN_HD Fe<FP> mul_chain(const Fe<FP>& a, const Fe<FP>& b) {
+    uint32_t X[8], Y[8];
+    mont_row<FP, true>(X, Y, a.v, b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i += 2) {
+        mont_row<FP, false>(Y, X, a.v, b.v[i]);
+        if (i + 1 < 8) mont_row<FP, false>(X, Y, a.v, b.v[i + 1]);
+    }
+    // roles now: X even (X[0] == 0), Y odd:  result limb k = X[k+1] + Y[k]
+    Fe<FP> r;
+    cc::add_cc(r.v[0], X[1], Y[0]);
+#pragma unroll
+    for (int k = 1; k < 7; ++k) cc::addc_cc(r.v[k], X[k + 1], Y[k]);
+    cc::addc(r.v[7], Y[7], 0);
+    reduce_once_cc<FP>(r.v);
+    return r;
+}
+
+template <class FP>
+EAGEN_HD Fe<FP> mul(const Fe<FP>& a, const Fe<FP>& b) {
+#if defined(__CUDA_ARCH__)
+    return mul_chain(a, b);
+#else
+    return mul_portable(a, b);
+#endif
 }
 
 template <class FP>

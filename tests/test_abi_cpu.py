@@ -62,12 +62,14 @@ def test_fft_precomp_matches_reference_tables_and_oracle(eagen, oracle):
 def test_host_field_arithmetic_matches_oracle(eagen, oracle, field):
     p, fid = pyref.FIELDS[field], pyref.FIELD_ID[field]
     rng = pyref.SplitMix64(100 + fid)
-    vals = [0, 1, p - 1, p - 2, 2, (1 << 255) % p, (1 << 128) - 1] + [rng.next_bits(4) % p for _ in range(40)]
+    vals = [0, 1, p - 1, p - 2, 2, (1 << 255) % p, (1 << 128) - 1, (1 << 256) % p, p >> 1] + [rng.next_bits(4) % p for _ in range(400)]
     arr = oracle.pack_felts(vals, p)
     for i in range(len(vals)):
         a, b = arr[i], arr[(i * 7 + 3) % len(vals)]
         for op in (0, 1, 2):
             assert (eagen.selftest_field(fid, op, a, b) == oracle.field_op(fid, op, a, b)).all(), (field, op, i)
+        # op 6: the device's carry-chain Montgomery product, carry flag emulated on the host
+        assert (eagen.selftest_field(fid, 6, a, b) == oracle.field_op(fid, 2, a, b)).all(), (field, 'chain', i)
         assert (eagen.selftest_field(fid, 3, a) == oracle.field_op(fid, 3, a)).all()
         assert (eagen.selftest_field(fid, 5, a) == oracle.field_op(fid, 5, a)).all()
     # raw canonical limbs -> Montgomery
