@@ -1,0 +1,178 @@
+// eagen_msm.hpp -- C++17 host-side mirror of the reference crate's public API for the witness path, header-only over
+// the C ABI in eagen_msm.h.  The reference is Rust and no Rust toolchain exists in the build image, so this is the
+// compiled-language host layer a caller links against (the Rust shim in halo2-liam-eagen-msm_b200/rust/ has the same
+// shape).  Names, argument meaning and error behaviour follow the reference:
+//
+//   eagen::argument_witness_calc::compute_lhs_witness      src/argument_witness_calc.rs:87-136
+//   eagen::argument_witness_calc::precompute_multiplicities  :43-51
+//   eagen::argument_witness_calc::num_digits               :89-91 (order / isqrt / logb_ceil)
+//   eagen::negbase_utils::negbase_decompose                src/negbase_utils.rs:20-36 (+ pad/reverse, batched)
+//   eagen::negbase_utils::id_by_digit / digit_by_id        :46-56
+//   eagen::regular_functions_utils::{Polynomial, RegularFunction, compute_divisor_witness(_partial), FftPrecomp}
+//                                                          src/regular_functions_utils.rs:17-47,209-273,453-480
+//
+// Where the reference panics, these functions throw eagen::Error carrying the ABI status.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+#include "eagen_msm.h"
+
+namespace eagen {
+
+using Felt = std::array<uint64_t, 4>;            // Montgomery limbs, little endian
+using JacobianPoint = std::array<uint64_t, 12>;  // x | y | z
+using AffinePoint = std::array<uint64_t, 8>;     // x | y, identity = zeros
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+
+class Context {
+public:
+    explicit Context(eagen_curve curve, int device = 0) : curve_(curve) {
+        int rc = eagen_ctx_create(curve, device, &ctx_);
+        if (rc != EAGEN_OK) throw Error(rc, std::string("eagen_ctx_create: ") + eagen_status_string(rc));
+    }
+    ~Context() { eagen_ctx_destroy(ctx_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    eagen_ctx* raw() const { return ctx_; }
+    eagen_curve curve() const { return curve_; }
+    void check(int rc) const { if (rc != EAGEN_OK) throw Error(rc, eagen_last_error(ctx_)); }
+
+private:
+    eagen_ctx* ctx_ = nullptr;
+    eagen_curve curve_;
+};
+
+namespace regular_functions_utils {
+
+// reference: trait FftPrecomp, src/regular_functions_utils.rs:17-24
+struct FftPrecomp {
+    static Felt omega_pow(eagen_curve c, uint32_t exp2) { Felt o; eagen_fft_precomp(c, 0, exp2, o.data()); return o; }
+    static Felt omega_pow_inv(eagen_curve c, uint32_t exp2) { Felt o; eagen_fft_precomp(c, 1, exp2, o.data()); return o; }
+    static Felt half_pow(eagen_curve c, uint64_t exp) { Felt o; eagen_fft_precomp(c, 2, exp, o.data()); return o; }
+};
+
+// reference: struct Polynomial { pub poly: Vec<F> }, :26-29; coefficients low degree first
+struct Polynomial {
+    std::vector<Felt> poly;
+    Polynomial() {}
+    explicit Polynomial(std::vector<Felt> p) : poly(std::move(p)) {}
+    // &Polynomial * &Polynomial, :209-216
+    Polynomial mul(const Context& ctx, const Polynomial& o) const {
+        if (poly.empty() && o.poly.empty()) return Polynomial();
+        std::vector<Felt> out(poly.size() + o.poly.size() - 1);
+        ctx.check(eagen_poly_mul(ctx.raw(), poly.empty() ? nullptr : poly[0].data(), poly.size(),
+                                 o.poly.empty() ? nullptr : o.poly[0].data(), o.poly.size(), out.empty() ? nullptr : out[0].data()));
+        return Polynomial(std::move(out));
+    }
+};
+
+// reference: struct RegularFunction { a, b } = a(x) + y b(x), :220-225
+struct RegularFunction {
+    Polynomial a, b;
+    // reference: RegularFunction::ev, :228-237 (batched over points; identity points evaluate to 0)
+    std::vector<Felt> ev(const Context& ctx, const std::vector<JacobianPoint>& pts) const {
+        std::vector<Felt> out(pts.size());
+        if (pts.empty()) return out;
+        ctx.check(eagen_eval_function(ctx.raw(), a.poly.empty() ? nullptr : a.poly[0].data(), a.poly.size(),
+                                      b.poly.empty() ? nullptr : b.poly[0].data(), b.poly.size(), pts[0].data(), pts.size(), out[0].data()));
+        return out;
+    }
+};
+
+inline RegularFunction function_from_result(eagen_result* r, size_t k) {
+    RegularFunction f;
+    f.a.poly.resize(eagen_result_poly_len(r, k, EAGEN_POLY_A));
+    f.b.poly.resize(eagen_result_poly_len(r, k, EAGEN_POLY_B));
+    if (!f.a.poly.empty()) eagen_result_poly_copy(r, k, EAGEN_POLY_A, f.a.poly[0].data());
+    if (!f.b.poly.empty()) eagen_result_poly_copy(r, k, EAGEN_POLY_B, f.b.poly[0].data());
+    return f;
+}
+
+// reference: compute_divisor_witness_partial, :453-467
+inline std::pair<RegularFunction, AffinePoint> compute_divisor_witness_partial(const Context& ctx, const std::vector<JacobianPoint>& pts,
+                                                                               uint32_t flags = EAGEN_CANONICAL) {
+    eagen_result* r = nullptr;
+    AffinePoint out{};
+    ctx.check(eagen_divisor_witness(ctx.raw(), pts.empty() ? nullptr : pts[0].data(), pts.size(), flags | EAGEN_PARTIAL, out.data(), &r));
+    RegularFunction f = function_from_result(r, 0);
+    eagen_result_free(r);
+    return {std::move(f), out};
+}
+// reference: compute_divisor_witness, :476-480 (throws EAGEN_E_SUM_NONZERO where the reference panics)
+inline RegularFunction compute_divisor_witness(const Context& ctx, const std::vector<JacobianPoint>& pts, uint32_t flags = EAGEN_CANONICAL) {
+    eagen_result* r = nullptr;
+    ctx.check(eagen_divisor_witness(ctx.raw(), pts.empty() ? nullptr : pts[0].data(), pts.size(), flags & ~(uint32_t)EAGEN_PARTIAL, nullptr, &r));
+    RegularFunction f = function_from_result(r, 0);
+    eagen_result_free(r);
+    return f;
+}
+
+}  // namespace regular_functions_utils
+
+namespace negbase_utils {
+
+// reference: id_by_digit / digit_by_id, src/negbase_utils.rs:46-56
+inline std::optional<size_t> id_by_digit(uint8_t digit) { if (digit == 0) return std::nullopt; return (size_t)(digit - 1); }
+inline uint8_t digit_by_id(size_t id) { return (uint8_t)(id + 1); }
+
+// reference: negbase_decompose + pad + reverse for n scalars (src/negbase_utils.rs:20-36, argument_witness_calc.rs:99-101):
+// n x d digits, most significant first
+inline std::vector<uint8_t> negbase_decompose(const Context& ctx, const std::vector<Felt>& scalars, uint8_t base, uint32_t* d_out = nullptr) {
+    uint32_t d = 0;
+    ctx.check(eagen_num_digits(ctx.curve(), base, &d));
+    std::vector<uint8_t> digits(scalars.size() * d);
+    ctx.check(eagen_negbase_decompose(ctx.raw(), scalars.empty() ? nullptr : scalars[0].data(), scalars.size(), base, digits.data()));
+    if (d_out) *d_out = d;
+    return digits;
+}
+
+}  // namespace negbase_utils
+
+namespace argument_witness_calc {
+
+// d = logb_ceil(isqrt(order)+2, base) + 1, reference: :32-40,54-56,89-91
+inline uint32_t num_digits(eagen_curve curve, uint8_t base) {
+    uint32_t d = 0;
+    int rc = eagen_num_digits(curve, base, &d);
+    if (rc != EAGEN_OK) throw Error(rc, eagen_status_string(rc));
+    return d;
+}
+
+// reference: precompute_multiplicities, :43-51 (n points at once; out[j*(base-1) + k-1] = k * P_j, affine)
+inline std::vector<AffinePoint> precompute_multiplicities(const Context& ctx, const std::vector<JacobianPoint>& pts, uint8_t base) {
+    std::vector<AffinePoint> out(pts.size() * (size_t)(base - 1));
+    if (!pts.empty()) ctx.check(eagen_precompute_multiplicities(ctx.raw(), pts[0].data(), pts.size(), base, out[0].data()));
+    return out;
+}
+
+struct LhsWitness {
+    AffinePoint carry;                                              // sum s_j P_j
+    std::vector<regular_functions_utils::RegularFunction> functions;  // index k <-> coefficient of (-base)^k
+};
+
+// reference: compute_lhs_witness, :87-136
+inline LhsWitness compute_lhs_witness(const Context& ctx, const std::vector<Felt>& scalars, const std::vector<JacobianPoint>& pts, uint8_t base,
+                                      uint32_t flags = EAGEN_CANONICAL) {
+    if (scalars.size() != pts.size()) throw Error(EAGEN_E_LEN, "incompatible amount of coefficients");  // :88
+    eagen_result* r = nullptr;
+    ctx.check(eagen_lhs_witness(ctx.raw(), scalars.empty() ? nullptr : scalars[0].data(), pts.empty() ? nullptr : pts[0].data(), pts.size(),
+                                base, flags, &r));
+    LhsWitness w;
+    eagen_result_carry(r, w.carry.data());
+    size_t nf = eagen_result_num_functions(r);
+    for (size_t k = 0; k < nf; ++k) w.functions.push_back(regular_functions_utils::function_from_result(r, k));
+    eagen_result_free(r);
+    return w;
+}
+
+}  // namespace argument_witness_calc
+}  // namespace eagen

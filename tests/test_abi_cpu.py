@@ -128,3 +128,14 @@ def test_ntt_pass_plan(eagen):
             assert 1 <= hi - lo + 1 <= 10
             stages += list(range(hi, lo - 1, -1))
         assert stages == list(range(t - 1, -1, -1))
+
+
+def test_cpp_host_mirror_compiles_links_and_runs(eagen, tmp_path):
+    """include/eagen_msm.hpp (the C++ mirror of the reference API) builds against the library and its GPU-free calls work"""
+    import subprocess
+    exe = str(tmp_path / "host_mirror_check")
+    libdir = os.path.dirname(eagen.LIB_PATH)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "host_mirror_check.cpp"),
+                           "-L", libdir, "-leagen_msm", "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
