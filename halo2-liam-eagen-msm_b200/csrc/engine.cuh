@@ -533,7 +533,7 @@ private:
     DevBuf in_scalars_, in_points_, planes_, rows_, table_, sums_, partials_, carries_, carries_proj_;
     DevBuf cnt_, tree_n_, tree_of_pos_, tpts_;
     std::unique_ptr<Scope> prof_scope_;
-    DevBuf ptlev_, lvlcnt_, a_[2], b_[2], ea_, eb_, oa_, ob_, den_, binv_, desc_, tops_, lead_;
+    DevBuf ptlev_, lvlcnt_, a_[2], b_[2], ea_, eb_, oa_, ob_, wk_, top_, twist_, den_, binv_, desc_, tops_, lead_;
 
     void use() { EAGEN_CUDA(cudaSetDevice(dev_)); }
 
@@ -606,7 +606,8 @@ private:
 
     // batched transform of n_tr arrays of size 2^t living in `data`; optional compact gather / scatter
     void ntt(bool inverse, F* data, const F* src, size_t src_stride, int src_len, F* dst, size_t dst_stride, int dst_len,
-             int t, size_t n_tr, const int* counts, int node_max, size_t n_present = (size_t)-1) {
+             int t, size_t n_tr, const int* counts, int node_max, size_t n_present = (size_t)-1,
+             const F* twist = nullptr, const F* sub_top = nullptr, size_t dst_off = 0) {
         if (n_present == (size_t)-1) n_present = n_tr;
         {   // algorithmic work: every present element is read and written once per pass, t/2 modmul per element in total
             std::vector<std::pair<int, int>> pl = ntt_plan(t);
@@ -614,7 +615,7 @@ private:
             double bytes = 64.0 * el * pl.size();
             if (src) bytes -= 32.0 * el - 32.0 * (double)n_present * src_len;
             if (dst) bytes -= 32.0 * el - 32.0 * (double)n_present * dst_len;
-            prof_scope_.reset(new Scope(this, inverse ? "ntt_inverse" : "ntt_forward", bytes, el * t / 2.0));
+            prof_scope_.reset(new Scope(this, inverse ? "ntt_inverse" : "ntt_forward", bytes, el * t / 2.0 + (twist ? el : 0.0)));
         }
         struct Closer { std::unique_ptr<Scope>& s; ~Closer() { s.reset(); } } closer{prof_scope_};
         NttPass<FB> a;
@@ -627,7 +628,10 @@ private:
         for (size_t p = 0; p < plan.size(); ++p) {
             a.s_hi = plan[p].first; a.s_lo = plan[p].second;
             a.src = (p == 0) ? src : nullptr;
+            a.twist = (p == 0) ? twist : nullptr;
             a.dst = (p + 1 == plan.size()) ? dst : nullptr;
+            a.sub_top = (p + 1 == plan.size()) ? sub_top : nullptr;
+            a.dst_off = dst_off;
             if (inverse) k_ntt_pass<FB, true><<<(unsigned)tiles, NTT_THREADS, 0, st_>>>(a);
             else k_ntt_pass<FB, false><<<(unsigned)tiles, NTT_THREADS, 0, st_>>>(a);
             ++launches_;
@@ -734,14 +738,14 @@ private:
     }
 
     size_t pooled_bytes() const {
-        return tpts_.cap + ptlev_.cap + a_[0].cap + a_[1].cap + b_[0].cap + b_[1].cap + ea_.cap + eb_.cap + oa_.cap + ob_.cap + den_.cap + binv_.cap + desc_.cap;
+        return tpts_.cap + ptlev_.cap + a_[0].cap + a_[1].cap + b_[0].cap + b_[1].cap + ea_.cap + eb_.cap + oa_.cap + ob_.cap + wk_.cap + den_.cap + binv_.cap + desc_.cap;
     }
     // working-set estimate per tree of n points (bytes)
     static size_t tree_bytes(size_t n) {
         size_t lc = (n + 1) / 2;
         size_t L = (size_t)ceil_log2(lc);
         size_t pad = lc + ((size_t)1 << L) + 8;  // slack for the +1 slots and the top levels
-        return n * 64 + 2 * lc * 64 + pad * 32 * (4 + 4 + 2 + 3) + lc * sizeof(MergeDesc<FB>) / 2 + 4096;
+        return n * 64 + 2 * lc * 64 + pad * 32 * (4 + 8 + 2 + 3) + lc * sizeof(MergeDesc<FB>) / 2 + 4096;
     }
 
     // Divisor witnesses of `nt` point lists (T + tree*cap, counts cnts[tree]) -> res slots.
@@ -791,8 +795,13 @@ private:
         Aff* PT = (Aff*)ptlev_.ensure(pt_total * sizeof(Aff));
         F* A[2] = {(F*)a_[0].ensure(szA * 32), (F*)a_[1].ensure(szA * 32)};
         F* B[2] = {(F*)b_[0].ensure(szB * 32), (F*)b_[1].ensure(szB * 32)};
-        F* EA = (F*)ea_.ensure(std::max<size_t>(szE, 1) * 32); F* EB = (F*)eb_.ensure(std::max<size_t>(szE, 1) * 32);
-        F* OA = (F*)oa_.ensure(std::max<size_t>(szO, 1) * 32); F* OB = (F*)ob_.ensure(std::max<size_t>(szO, 1) * 32);
+        // evaluation buffers are double-buffered: the merge of level l writes the parents' evaluations straight into the
+        // first half of level l+1's buffers; W is the in-place workspace of the coset and inverse transforms
+        F* EA[2] = {(F*)ea_.ensure(std::max<size_t>(szE, 1) * 32), (F*)oa_.ensure(std::max<size_t>(szE, 1) * 32)};
+        F* EB[2] = {(F*)eb_.ensure(std::max<size_t>(szE, 1) * 32), (F*)ob_.ensure(std::max<size_t>(szE, 1) * 32)};
+        F* W = (F*)wk_.ensure(std::max<size_t>(szO, 1) * 32);
+        F* TOP = (F*)top_.ensure(std::max<size_t>((size_t)nt * (L ? node_max[1] : 1), 1) * 32);
+        F* TWIST = (F*)twist_.ensure(((size_t)1 << (L > 0 ? L - 1 : 0)) * 32);
         F* den = (F*)den_.ensure(std::max<size_t>(std::max(szO, (size_t)nt * node_max[0]), 1) * 32);
         MergeDesc<FB>* desc = (MergeDesc<FB>*)desc_.ensure(std::max<size_t>((size_t)nt * (L ? node_max[1] : 1), 1) * sizeof(MergeDesc<FB>));
         if (L) ensure_twiddles(L);
@@ -814,7 +823,11 @@ private:
             launch(k_leaf_lines<FB>, w0, 256, T, cap, (const int*)dlv, (const Aff*)(PT + pt_off[0]), node_max[0], nt, A[0], B[0]);
         }
 
-        int cur = 0;
+        int cur = 0, e = 0;
+        if (L > 0) {  // the leaves' evaluations on the 2-point domain (full forward transform, true coefficients)
+            ntt(false, EA[0], A[0], 2, 2, nullptr, 0, 0, 1, (size_t)nt * node_max[0], cnt_of(0), (int)node_max[0], (size_t)present[0]);
+            ntt(false, EB[0], B[0], 1, 1, nullptr, 0, 0, 1, (size_t)nt * node_max[0], cnt_of(0), (int)node_max[0], (size_t)present[0]);
+        }
         for (int l = 0; l < L; ++l) {
             const int t = l + 1;
             const size_t m = (size_t)1 << l, Tn = 2 * m;
@@ -829,16 +842,26 @@ private:
                 launch(k_pair_den<FB>, wm, 256, (const Aff*)Pc, nodes, cnt_of(l), merges, nt, den);
             }
             batch_invert(den, wm);
-            F tinv = half_pow(t);
             {
                 Scope ps(this, "pair_points", present[l + 1] * (128.0 + 32.0 + 64.0 + 192.0 + 272.0), present[l + 1] * (4.0 + 5.0));
                 launch(k_pair_finish<FB>, wm, 256, (const Aff*)Pc, nodes, cnt_of(l), merges, nt, (const F*)den, 0, Pp);
-                launch(k_merge_desc<FB>, wm, 128, (const Aff*)Pc, nodes, cnt_of(l), (const Aff*)Pp, merges, nt, tinv, desc);
+                launch(k_merge_desc<FB>, wm, 128, (const Aff*)Pc, nodes, cnt_of(l), (const Aff*)Pp, merges, nt, F::one(), desc);
             }
-            // children -> evaluation domain
-            ntt(false, EA, A[cur], m + 1, (int)(m + 1), nullptr, 0, 0, t, (size_t)nt * nodes, cnt_of(l), (int)nodes, (size_t)present[l]);
-            ntt(false, EB, B[cur], m, (int)m, nullptr, 0, 0, t, (size_t)nt * nodes, cnt_of(l), (int)nodes, (size_t)present[l]);
-            // pointwise merge with exact division
+            // Children in the evaluation domain.  Positions [0, m) of each child's 2m-point buffer already hold its values on the
+            // m-point domain (written by the previous level's merge); only the odd coset w_T * w_m^k is transformed here:
+            // a(x) = sum_{i<m} c_i x^i + c_m x^m and x^m = -1 on the coset, so values = NTT_m(c_i w_T^i) - c_m.
+            // Stored coefficients carry the factor s = m of the unscaled inverse transform; the twist table removes it.
+            if (l > 0) {
+                {
+                    Scope ps(this, "ntt_forward", (double)m * 64.0, (double)m);
+                    launch(k_gen_twist<FB>, m, 256, tw(false, t), m, half_pow(l), TWIST);
+                }
+                ntt(false, W, A[cur], m + 1, (int)m, EA[e], Tn, (int)m, l, (size_t)nt * nodes, cnt_of(l), (int)nodes, (size_t)present[l],
+                    (const F*)TWIST, (const F*)TOP, m);
+                ntt(false, W, B[cur], m, (int)m, EB[e], Tn, (int)m, l, (size_t)nt * nodes, cnt_of(l), (int)nodes, (size_t)present[l],
+                    (const F*)TWIST, nullptr, m);
+            }
+            // pointwise merge with exact division; parents' evaluations go to the next level's buffers (stride 2T)
             {
                 Scope ps(this, "merge_den", pts * 32.0, pts * 1.0);
                 launch(k_den<FB>, wm << t, 256, (const MergeDesc<FB>*)desc, wm, t, tw(false, t), den, d_err_);
@@ -846,17 +869,19 @@ private:
             batch_invert(den, wm << t);
             {
                 Scope ps(this, "merge_pointwise", pts * 224.0, pts * 15.0);
-                launch(k_pointwise<CC>, wm << t, 128, (const MergeDesc<FB>*)desc, wm, t, tw(false, t), tinv, (const F*)EA, (const F*)EB,
-                       (const F*)den, merges, nodes, OA, OB);
+                launch(k_pointwise<CC>, wm << t, 128, (const MergeDesc<FB>*)desc, wm, t, tw(false, t), (const F*)EA[e], (const F*)EB[e],
+                       (const F*)den, merges, nodes, EA[e ^ 1], EB[e ^ 1], 2 * Tn);
             }
-            // back to coefficients, compact parent slots
-            ntt(true, OA, nullptr, 0, 0, A[cur ^ 1], Tn + 1, (int)Tn, t, wm, cnt_of(l + 1), (int)merges, (size_t)present[l + 1]);
-            ntt(true, OB, nullptr, 0, 0, B[cur ^ 1], Tn, (int)Tn, t, wm, cnt_of(l + 1), (int)merges, (size_t)present[l + 1]);
+            // back to coefficients (unscaled: stored = T * true), compact parent slots
+            ntt(true, W, EA[e ^ 1], 2 * Tn, (int)Tn, A[cur ^ 1], Tn + 1, (int)Tn, t, wm, cnt_of(l + 1), (int)merges, (size_t)present[l + 1]);
+            ntt(true, W, EB[e ^ 1], 2 * Tn, (int)Tn, B[cur ^ 1], Tn, (int)Tn, t, wm, cnt_of(l + 1), (int)merges, (size_t)present[l + 1]);
             {
-                Scope ps(this, "merge_fixup", present[l + 1] * (6 * 32.0 + 64.0), present[l + 1] * 5.0);
-                launch(k_fixup<FB>, wm, 128, (const MergeDesc<FB>*)desc, wm, t, merges, nodes, (const F*)A[cur], (const F*)B[cur], A[cur ^ 1]);
+                Scope ps(this, "merge_fixup", present[l + 1] * (6 * 32.0 + 96.0), present[l + 1] * 7.0);
+                F kc = l == 0 ? F::one() : half_pow(2 * l);
+                launch(k_fixup<FB>, wm, 128, (const MergeDesc<FB>*)desc, wm, t, merges, nodes, (const F*)A[cur], (const F*)B[cur], A[cur ^ 1],
+                       kc, from_u32<FB>((uint32_t)Tn), TOP);
             }
-            cur ^= 1;
+            cur ^= 1; e ^= 1;
         }
         // roots: one node per tree at level L (node_max[L] == 1)
         const size_t ra = ((size_t)1 << L) + 1, rb = (size_t)1 << L;
@@ -864,6 +889,10 @@ private:
         EAGEN_CUDA(cudaMemsetAsync(tops, 0, (size_t)2 * nt * sizeof(int), st_));
         Scope ps_can(this, "canonical_form", (double)nt * (double)(ra + rb) * 32.0 * ((flags & EAGEN_RAW_TREE) ? 1.0 : 3.0),
                      (flags & EAGEN_RAW_TREE) ? 0.0 : (double)nt * (double)(ra + rb));
+        if ((flags & EAGEN_RAW_TREE) && L > 0) {  // stored root = 2^L * true coefficients
+            launch2d(k_scale_const<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, A[cur], ra, (int)ra, half_pow(L));
+            launch2d(k_scale_const<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, B[cur], rb, (int)rb, half_pow(L));
+        }
         launch2d(k_find_top<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, (const F*)A[cur], ra, (int)ra, tops);
         launch2d(k_find_top<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, (const F*)B[cur], rb, (int)rb, tops + nt);
         if (!(flags & EAGEN_RAW_TREE)) {

@@ -537,9 +537,11 @@ struct NttPass {
     const Fe<FP>* src;       // optional compact source (first forward pass)
     Fe<FP>* dst;             // optional compact destination (last inverse pass)
     const Fe<FP>* tw;        // tw[e] = w_T^e (or w_T^-e), e < T/2
+    const Fe<FP>* twist;     // optional: element i of the gathered source is multiplied by twist[i] (coset transform)
+    const Fe<FP>* sub_top;   // optional: sub_top[transform] is subtracted from every scattered output
     const int* counts;       // transforms present per tree
     size_t total;            // n_transforms * T
-    size_t src_stride, dst_stride;
+    size_t src_stride, dst_stride, dst_off;
     int src_len, dst_len;
     int node_max;            // transforms per tree (stride of the tree index)
     int t, s_hi, s_lo;
@@ -579,7 +581,12 @@ k_ntt_pass(NttPass<FP> a) {
             live[r] = node < a.counts[tree];
             if (live[r]) {
                 size_t i = lin[r] & Tmask;
-                if (a.src) { if ((int)i < a.src_len) v = ldg(a.src + tr * a.src_stride + i); }
+                if (a.src) {
+                    if ((int)i < a.src_len) {
+                        v = ldg(a.src + tr * a.src_stride + i);
+                        if (a.twist) v = mul(v, ldg(a.twist + i));
+                    }
+                }
                 else v = ldg(a.data + lin[r]);
             }
         }
@@ -623,7 +630,10 @@ k_ntt_pass(NttPass<FP> a) {
         Fe<FP> v = s[(E << lw) | wl];
         if (a.dst) {
             size_t tr = lin[r] >> a.t, i = lin[r] & Tmask;
-            if ((int)i < a.dst_len) stg(a.dst + tr * a.dst_stride + i, v);
+            if ((int)i < a.dst_len) {
+                if (a.sub_top) v = sub(v, ldg(a.sub_top + tr));
+                stg(a.dst + tr * a.dst_stride + a.dst_off + i, v);
+            }
         } else {
             stg(a.data + lin[r], v);
         }
@@ -678,12 +688,15 @@ __global__ void k_den(const MergeDesc<FP>* __restrict__ desc, size_t nmerges, in
     stg(den + g, dv);
 }
 
+// Writes the parents' TRUE evaluations on the T-point domain, in the layout of the next level's evaluation buffers
+// (parent m at m*out_stride, out_stride = 2T): positions [0, T) of a 2T-point bit-reversed transform are exactly the
+// T-point domain in bit-reversed order, so the next level only has to add the odd coset (see Engine::run_trees).
 template <class CC>
 __global__ void k_pointwise(const MergeDesc<typename CC::Base>* __restrict__ desc, size_t nmerges, int t,
-                            const Fe<typename CC::Base>* __restrict__ tw, Fe<typename CC::Base> tinv,
+                            const Fe<typename CC::Base>* __restrict__ tw,
                             const Fe<typename CC::Base>* __restrict__ EA, const Fe<typename CC::Base>* __restrict__ EB,
                             const Fe<typename CC::Base>* __restrict__ dinv, size_t merges_per_tree, size_t nodes_per_tree,
-                            Fe<typename CC::Base>* __restrict__ OA, Fe<typename CC::Base>* __restrict__ OB) {
+                            Fe<typename CC::Base>* __restrict__ OA, Fe<typename CC::Base>* __restrict__ OB, size_t out_stride) {
     typedef typename CC::Base F;
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (nmerges << t)) return;
@@ -696,18 +709,17 @@ __global__ void k_pointwise(const MergeDesc<typename CC::Base>* __restrict__ des
     Fe<F> a1 = ldg(EA + c1), b1 = ldg(EB + c1);
     Fe<F> ra, rb;
     if (mode == MERGE_PASS) {
-        ra = mul(a1, tinv); rb = mul(b1, tinv);
+        ra = a1; rb = b1;
     } else {
         Fe<F> a2 = ldg(EA + c2), b2 = ldg(EB + c2);
         Fe<F> x = eval_point(tw, t, p);
         Fe<F> gx = add(mul(sqr(x), x), CC::b());
         if (mode == MERGE_SHORTCUT) {
-            a1 = mul(a1, tinv); b1 = mul(b1, tinv);
             ra = add(mul(a1, a2), mul(mul(b1, b2), gx));
             rb = add(mul(a1, b2), mul(b1, a2));
         } else {
-            Fe<F> lam = add(ldg(&desc[m].slz), mul(ldg(&desc[m].slx), x));
-            Fe<F> ly = ldg(&desc[m].sly);
+            Fe<F> lam = add(ldg(&desc[m].lz), mul(ldg(&desc[m].lx), x));
+            Fe<F> ly = ldg(&desc[m].ly);
             Fe<F> lyg = mul(ly, gx);
             Fe<F> U = add(mul(a2, lam), mul(b2, lyg));
             Fe<F> V = add(mul(a2, ly), mul(b2, lam));
@@ -716,17 +728,20 @@ __global__ void k_pointwise(const MergeDesc<typename CC::Base>* __restrict__ des
             rb = mul(add(mul(a1, V), mul(b1, U)), di);
         }
     }
-    stg(OA + g, ra);
-    stg(OB + g, rb);
+    stg(OA + m * out_stride + p, ra);
+    stg(OB + m * out_stride + p, rb);
 }
 
 // The parent's a has T+1 coefficients but the transform has T points: the top coefficient q_T aliases
 // onto coefficient 0.  q_T has a closed form in the children's top coefficients, so compute it, subtract it
 // from coefficient 0 and store it at index T.
+// Scaling: the inverse transforms are unscaled, so the stored coefficients of a level are s * (true coefficients)
+// with s = (size of the transform that produced them) (1 for the leaves).  kc = 1/s_children^2 brings the closed form
+// back to the true q_T (written to `top` for the next level's coset transform); the stored copy is T * q_T.
 template <class FP>
 __global__ void k_fixup(const MergeDesc<FP>* __restrict__ desc, size_t nmerges, int t, size_t merges_per_tree, size_t nodes_per_tree,
                         const Fe<FP>* __restrict__ A, const Fe<FP>* __restrict__ B /* children, slots m+1 / m */,
-                        Fe<FP>* __restrict__ PA /* parent a, slot T+1 */) {
+                        Fe<FP>* __restrict__ PA /* parent a, slot T+1 */, Fe<FP> kc, Fe<FP> kT, Fe<FP>* __restrict__ top) {
     size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= nmerges) return;
     uint32_t mode = desc[m].mode;
@@ -748,9 +763,33 @@ __global__ void k_fixup(const MergeDesc<FP>* __restrict__ desc, size_t nmerges, 
             q = mul(a1t, a2t);
             if (h >= 2) q = add(q, add(mul(b1t, ldg(b2 + h - 2)), mul(ldg(b1 + h - 2), b2t)));
         }
+        q = mul(q, kc);
+    } else {
+        // pass-through: the parent IS the child, whose true top coefficient (index h of T+1, zero above) needs no alias fix
+        q = Fe<FP>::zero();
     }
-    stg(pa, sub(ldg(pa), q));
-    stg(pa + T, q);
+    Fe<FP> qs = mul(q, kT);
+    stg(pa, sub(ldg(pa), qs));
+    stg(pa + T, qs);
+    stg(top + m, q);
+}
+
+// twist[i] = w_{2T}^i * scale, i < T  (tw2 = table of the 2T-point transform): the odd-coset pre-multiplier that also
+// undoes the s-scaling of stored coefficients
+template <class FP>
+__global__ void k_gen_twist(const Fe<FP>* __restrict__ tw2, size_t T, Fe<FP> scale, Fe<FP>* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < T) stg(out + i, mul(ldg(tw2 + i), scale));
+}
+
+// out[i] *= c (root rescale in raw mode)
+template <class FP>
+__global__ void k_scale_const(Fe<FP>* __restrict__ coef, size_t stride, int len, Fe<FP> c) {
+    int tree = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    Fe<FP>* q = coef + (size_t)tree * stride + i;
+    stg(q, mul(ldg(q), c));
 }
 
 // ------------------------------------------------------------------------------------------------
