@@ -225,7 +225,39 @@ inline void sub_cc(uint32_t& d, uint32_t a, uint32_t b) { uint64_t t = (uint64_t
 inline void subc_cc(uint32_t& d, uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - CF; d = (uint32_t)t; CF = (uint32_t)((t >> 32) & 1); }
 inline void subc(uint32_t& d, uint32_t a, uint32_t b) { d = a - b - CF; }
 #endif
+#if defined(__CUDA_ARCH__)
+EAGEN_D void neg32(uint32_t& d, uint32_t a) { asm volatile("sub.u32 %0, 0, %1;" : "=r"(d) : "r"(a)); }
+// a constant moved through a register so that ptxas keeps the mad.lo.cc/madc.hi.cc pair fusable into one IMAD.WIDE
+EAGEN_D uint32_t opaque(uint32_t c) { uint32_t r; asm("mov.b32 %0, %1;" : "=r"(r) : "r"(c)); return r; }  // not volatile: hoistable / CSE-able
+#else
+inline void neg32(uint32_t& d, uint32_t a) { d = 0u - a; }
+inline uint32_t opaque(uint32_t c) { return c; }
+#endif
 }  // namespace cc
+
+// (lo, hi) += c * m inside a carry chain, c a modulus limb (a compile-time constant once the caller's loop is unrolled).
+// Measured on B200 (tools/probe/pipe_probe.cu): IMAD.WIDE / IMAD.HI issue at 32 lanes/clk/SM, 32-bit IMAD at 64, IADD3 with
+// carry at 128 -- so limbs equal to 1 or a power of two are done with adds and shifts on the ALU pipe, zero limbs only
+// propagate the carry, and only the remaining limbs pay for a multiplier slot.
+EAGEN_HD void mad_const_pair(uint32_t& lo, uint32_t& hi, uint32_t c, uint32_t m, bool first, bool last) {
+    if (c == 0) {
+        cc::addc_cc(lo, lo, 0);
+        if (last) cc::addc(hi, hi, 0); else cc::addc_cc(hi, hi, 0);
+    } else if (c == 1) {
+        if (first) cc::add_cc(lo, lo, m); else cc::addc_cc(lo, lo, m);
+        if (last) cc::addc(hi, hi, 0); else cc::addc_cc(hi, hi, 0);
+    } else if ((c & (c - 1)) == 0) {
+        int k = 0;
+        while ((c >> k) != 1) ++k;
+        uint32_t l = m << k, h = m >> (32 - k);
+        if (first) cc::add_cc(lo, lo, l); else cc::addc_cc(lo, lo, l);
+        if (last) cc::addc(hi, hi, h); else cc::addc_cc(hi, hi, h);
+    } else {
+        uint32_t cr = cc::opaque(c);
+        if (first) cc::mad_lo_cc(lo, cr, m, lo); else cc::madc_lo_cc(lo, cr, m, lo);
+        if (last) cc::madc_hi(hi, cr, m, hi); else cc::madc_hi_cc(hi, cr, m, hi);
+    }
+}
 
 // One row of the interleaved (CIOS) Montgomery product on split accumulators.
 // The running sum is T = E + O*2^32 with E[0] == 0 on entry (E "even role": limb k = column k; O "odd role": limb k = column k+1).
@@ -257,33 +289,21 @@ EAGEN_HD void mont_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi)
         }
         cc::addc(E[7], E[7], 0);
     }
-    uint32_t m = O[0] * FP::INV;
-    // odd limbs of p onto the odd-role array; zero limbs only propagate the carry
+    // m = -T0 * p^-1 mod 2^32; the Pasta moduli are 1 mod 2^32, so m = -T0 (one ALU op instead of a multiply)
+    uint32_t m;
+    if (FP::INV == 0xffffffffu) cc::neg32(m, O[0]); else m = O[0] * FP::INV;
+    // odd limbs of p onto the odd-role array
     bool started = false;
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-        if (FP::mod(j + 1) != 0) {
-            if (!started) cc::mad_lo_cc(E[j], FP::mod(j + 1), m, E[j]); else cc::madc_lo_cc(E[j], FP::mod(j + 1), m, E[j]);
-            if (j == 6) cc::madc_hi(E[j + 1], FP::mod(j + 1), m, E[j + 1]); else cc::madc_hi_cc(E[j + 1], FP::mod(j + 1), m, E[j + 1]);
+        if (FP::mod(j + 1) != 0 || started) {
+            mad_const_pair(E[j], E[j + 1], FP::mod(j + 1), m, !started, j == 6);
             started = true;
-        } else if (started) {
-            cc::addc_cc(E[j], E[j], 0);
-            if (j == 6) cc::addc(E[j + 1], E[j + 1], 0); else cc::addc_cc(E[j + 1], E[j + 1], 0);
         }
     }
     // even limbs of p onto the even-role array (p[0] is odd, hence never zero); the carry out lands in column 8 = E[7]
-    cc::mad_lo_cc(O[0], FP::mod(0), m, O[0]);
-    cc::madc_hi_cc(O[1], FP::mod(0), m, O[1]);
 #pragma unroll
-    for (int j = 2; j < 8; j += 2) {
-        if (FP::mod(j) != 0) {
-            cc::madc_lo_cc(O[j], FP::mod(j), m, O[j]);
-            cc::madc_hi_cc(O[j + 1], FP::mod(j), m, O[j + 1]);
-        } else {
-            cc::addc_cc(O[j], O[j], 0);
-            cc::addc_cc(O[j + 1], O[j + 1], 0);
-        }
-    }
+    for (int j = 0; j < 8; j += 2) mad_const_pair(O[j], O[j + 1], FP::mod(j), m, j == 0, false);
     cc::addc(E[7], E[7], 0);
 }
 

@@ -925,7 +925,7 @@ __global__ void k_modmul_peak(Fe<FP>* out, int iters) {
     Fe<FP> a[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { a[i] = Fe<FP>::one(); a[i].v[0] += threadIdx.x * 4 + i; a[i].v[1] = blockIdx.x; }
-    Fe<FP> m = Fe<FP>::r2();
+    Fe<FP> m = ldg(out);  // runtime multiplier (a constant would be folded into immediates and is not what kernels see)
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) a[i] = mul(a[i], m);
