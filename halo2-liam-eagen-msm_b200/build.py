@@ -12,7 +12,7 @@ SOURCES = ["capi.cu", "engine_pallas.cu", "engine_vesta.cu", "engine_grumpkin.cu
 HEADERS = ["field.cuh", "curve.cuh", "kernels.cuh", "engine.cuh", "eagen_params.h", os.path.join("..", "..", "include", "eagen_msm.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "--expt-relaxed-constexpr", "-Xptxas", "-v"] + (os.environ.get("EAGEN_NVCC_EXTRA", "").split())
 
 
 def stale(target, deps):

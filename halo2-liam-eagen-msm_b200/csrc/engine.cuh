@@ -868,7 +868,7 @@ private:
             }
             batch_invert(den, wm << t);
             {
-                Scope ps(this, "merge_pointwise", pts * 224.0, pts * 15.0);
+                Scope ps(this, "merge_pointwise", pts * 224.0, pts * 13.0);
                 launch(k_pointwise<CC>, wm << t, 128, (const MergeDesc<FB>*)desc, wm, t, tw(false, t), (const F*)EA[e], (const F*)EB[e],
                        (const F*)den, merges, nodes, EA[e ^ 1], EB[e ^ 1], 2 * Tn);
             }

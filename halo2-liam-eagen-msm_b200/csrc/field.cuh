@@ -226,10 +226,12 @@ inline void subc_cc(uint32_t& d, uint32_t a, uint32_t b) { uint64_t t = (uint64_
 inline void subc(uint32_t& d, uint32_t a, uint32_t b) { d = a - b - CF; }
 #endif
 #if defined(__CUDA_ARCH__)
+EAGEN_D void ripple_cc(uint32_t& x) { asm volatile("addc.cc.u32 %0, %0, 0;" : "+r"(x)); }  // x += carry, chain continues
 EAGEN_D void neg32(uint32_t& d, uint32_t a) { asm volatile("sub.u32 %0, 0, %1;" : "=r"(d) : "r"(a)); }
 // a constant moved through a register so that ptxas keeps the mad.lo.cc/madc.hi.cc pair fusable into one IMAD.WIDE
 EAGEN_D uint32_t opaque(uint32_t c) { uint32_t r; asm("mov.b32 %0, %1;" : "=r"(r) : "r"(c)); return r; }  // not volatile: hoistable / CSE-able
 #else
+inline void ripple_cc(uint32_t& x) { addc_cc(x, x, 0); }
 inline void neg32(uint32_t& d, uint32_t a) { d = 0u - a; }
 inline uint32_t opaque(uint32_t c) { return c; }
 #endif
@@ -241,8 +243,8 @@ inline uint32_t opaque(uint32_t c) { return c; }
 // propagate the carry, and only the remaining limbs pay for a multiplier slot.
 EAGEN_HD void mad_const_pair(uint32_t& lo, uint32_t& hi, uint32_t c, uint32_t m, bool first, bool last) {
     if (c == 0) {
-        cc::addc_cc(lo, lo, 0);
-        if (last) cc::addc(hi, hi, 0); else cc::addc_cc(hi, hi, 0);
+        cc::ripple_cc(lo);
+        if (last) cc::addc(hi, hi, 0); else cc::ripple_cc(hi);
     } else if (c == 1) {
         if (first) cc::add_cc(lo, lo, m); else cc::addc_cc(lo, lo, m);
         if (last) cc::addc(hi, hi, 0); else cc::addc_cc(hi, hi, 0);

@@ -552,8 +552,11 @@ EAGEN_D uint32_t insert_zero_bit(uint32_t v, int pos) {
     return ((v >> pos) << (pos + 1)) | lo;
 }
 
+#ifndef EAGEN_NTT_MINBLOCKS
+#define EAGEN_NTT_MINBLOCKS 4
+#endif
 template <class FP, bool INVERSE>
-__global__ void __launch_bounds__(NTT_THREADS)
+__global__ void __launch_bounds__(NTT_THREADS, EAGEN_NTT_MINBLOCKS)
 k_ntt_pass(NttPass<FP> a) {
     __shared__ uint4 sm[NTT_TILE * 2];
     Fe<FP>* s = reinterpret_cast<Fe<FP>*>(sm);
@@ -594,7 +597,40 @@ k_ntt_pass(NttPass<FP> a) {
     }
     __syncthreads();
 
-    for (int st = 0; st < k; ++st) {
+    // Radix-4 rounds: two stages per shared-memory round trip, four elements per thread in registers (one barrier,
+    // one set of index computations and three twiddle loads for four butterflies; the two products of each half-round are
+    // independent, which doubles the instruction-level parallelism of the carry chains).
+    int st = 0;
+    for (; st + 1 < k; st += 2) {
+        const int slo = INVERSE ? st : (k - 2 - st);     // lower local stage of the pair (the other one is slo + 1)
+        const int bitpos = slo + lw;
+        const int sgl = a.s_lo + slo, sgh = sgl + 1;     // global stages
+        const uint32_t bq = threadIdx.x;
+        const uint32_t i0 = ((bq >> bitpos) << (bitpos + 2)) | (bq & ((1u << bitpos) - 1));
+        const uint32_t d = 1u << bitpos;
+        const uint32_t E = i0 >> lw, wl = i0 & ((1u << lw) - 1);
+        const size_t w = (tile << lw) + wl;
+        const size_t L = w & (((size_t)1 << a.s_lo) - 1);
+        const size_t jl = ((size_t)(E & ((1u << slo) - 1)) << a.s_lo) | L;   // index inside the 2^sgl group (same for all four)
+        const Fe<FP> W0 = ldg(a.tw + (jl << (a.t - 1 - sgl)));
+        const Fe<FP> W1a = ldg(a.tw + (jl << (a.t - 1 - sgh)));
+        const Fe<FP> W1b = ldg(a.tw + ((jl + ((size_t)1 << sgl)) << (a.t - 1 - sgh)));
+        Fe<FP> x0 = s[i0], x1 = s[i0 + d], x2 = s[i0 + 2 * d], x3 = s[i0 + 3 * d];
+        if (INVERSE) {   // decimation in time: stage slo (distance d), then stage slo+1 (distance 2d)
+            Fe<FP> v1 = mul(x1, W0), v3 = mul(x3, W0);
+            Fe<FP> y0 = add(x0, v1), y1 = sub(x0, v1), y2 = add(x2, v3), y3 = sub(x2, v3);
+            Fe<FP> u2 = mul(y2, W1a), u3 = mul(y3, W1b);
+            s[i0] = add(y0, u2); s[i0 + 2 * d] = sub(y0, u2);
+            s[i0 + d] = add(y1, u3); s[i0 + 3 * d] = sub(y1, u3);
+        } else {         // decimation in frequency: stage slo+1 (distance 2d), then stage slo (distance d)
+            Fe<FP> y0 = add(x0, x2), y2 = mul(sub(x0, x2), W1a);
+            Fe<FP> y1 = add(x1, x3), y3 = mul(sub(x1, x3), W1b);
+            s[i0] = add(y0, y1); s[i0 + d] = mul(sub(y0, y1), W0);
+            s[i0 + 2 * d] = add(y2, y3); s[i0 + 3 * d] = mul(sub(y2, y3), W0);
+        }
+        __syncthreads();
+    }
+    for (; st < k; ++st) {   // odd stage count: one radix-2 stage is left
         const int sigma = INVERSE ? st : (k - 1 - st);   // local stage
         const int sg = a.s_lo + sigma;                   // global stage
         const int bitpos = sigma + lw;
@@ -691,8 +727,12 @@ __global__ void k_den(const MergeDesc<FP>* __restrict__ desc, size_t nmerges, in
 // Writes the parents' TRUE evaluations on the T-point domain, in the layout of the next level's evaluation buffers
 // (parent m at m*out_stride, out_stride = 2T): positions [0, T) of a 2T-point bit-reversed transform are exactly the
 // T-point domain in bit-reversed order, so the next level only has to add the odd coset (see Engine::run_trees).
+#ifndef EAGEN_PW_MINBLOCKS
+#define EAGEN_PW_MINBLOCKS 8
+#endif
 template <class CC>
-__global__ void k_pointwise(const MergeDesc<typename CC::Base>* __restrict__ desc, size_t nmerges, int t,
+__global__ void __launch_bounds__(128, EAGEN_PW_MINBLOCKS)
+k_pointwise(const MergeDesc<typename CC::Base>* __restrict__ desc, size_t nmerges, int t,
                             const Fe<typename CC::Base>* __restrict__ tw,
                             const Fe<typename CC::Base>* __restrict__ EA, const Fe<typename CC::Base>* __restrict__ EB,
                             const Fe<typename CC::Base>* __restrict__ dinv, size_t merges_per_tree, size_t nodes_per_tree,
@@ -714,18 +754,22 @@ __global__ void k_pointwise(const MergeDesc<typename CC::Base>* __restrict__ des
         Fe<F> a2 = ldg(EA + c2), b2 = ldg(EB + c2);
         Fe<F> x = eval_point(tw, t, p);
         Fe<F> gx = add(mul(sqr(x), x), CC::b());
+        // products of the form (u + y v)(u' + y v') = (u u' + v v' g) + y (u v' + v u') with three multiplications for the
+        // cross term (Karatsuba): 4 instead of 5 field products each
         if (mode == MERGE_SHORTCUT) {
-            ra = add(mul(a1, a2), mul(mul(b1, b2), gx));
-            rb = add(mul(a1, b2), mul(b1, a2));
+            Fe<F> q1 = mul(a1, a2), q2 = mul(b1, b2), q3 = mul(add(a1, b1), add(a2, b2));
+            ra = add(q1, mul(q2, gx));
+            rb = sub(sub(q3, q1), q2);
         } else {
             Fe<F> lam = add(ldg(&desc[m].lz), mul(ldg(&desc[m].lx), x));
             Fe<F> ly = ldg(&desc[m].ly);
-            Fe<F> lyg = mul(ly, gx);
-            Fe<F> U = add(mul(a2, lam), mul(b2, lyg));
-            Fe<F> V = add(mul(a2, ly), mul(b2, lam));
+            Fe<F> p1 = mul(a2, lam), p2 = mul(b2, ly), p3 = mul(add(a2, b2), add(lam, ly));
+            Fe<F> U = add(p1, mul(p2, gx));
+            Fe<F> V = sub(sub(p3, p1), p2);
+            Fe<F> q1 = mul(a1, U), q2 = mul(b1, V), q3 = mul(add(a1, b1), add(U, V));
             Fe<F> di = ldg(dinv + g);
-            ra = mul(add(mul(a1, U), mul(mul(b1, gx), V)), di);
-            rb = mul(add(mul(a1, V), mul(b1, U)), di);
+            ra = mul(add(q1, mul(q2, gx)), di);
+            rb = mul(sub(sub(q3, q1), q2), di);
         }
     }
     stg(OA + m * out_stride + p, ra);
