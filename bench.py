@@ -24,6 +24,17 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "Eagen-MSM witness points/sec at 2^20 Pallas, 1/2/4/8 B200 vs host CPU"
+
+# stdout carries exactly ONE JSON line (rank 0): everything else that libraries print to fd 1 (e.g. NCCL's version banner)
+# is redirected to stderr for the lifetime of the process.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
 UNIT = "points/s"
 BASE = 5
 
@@ -135,7 +146,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -311,7 +322,7 @@ def main():
         "kernel_shares": shares,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

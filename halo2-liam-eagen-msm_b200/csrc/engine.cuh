@@ -529,7 +529,7 @@ private:
     int* d_one_ = nullptr;
     uint64_t launches_ = 0;
     int tw_max_ = 0;
-    DevBuf tw_fwd_, tw_inv_;
+    DevBuf tw_fwd_, tw_inv_, xt_, gt_;
     DevBuf in_scalars_, in_points_, planes_, rows_, table_, sums_, partials_, carries_, carries_proj_;
     DevBuf cnt_, tree_n_, tree_of_pos_, tpts_;
     std::unique_ptr<Scope> prof_scope_;
@@ -580,8 +580,13 @@ private:
         F* i = (F*)tw_inv_.ensure(cnt * 32);
         launch(k_gen_twiddles<FB>, cnt, 256, f, t, 0);
         launch(k_gen_twiddles<FB>, cnt, 256, i, t, 1);
+        F* xt = (F*)xt_.ensure(2 * cnt * 32);
+        F* gt = (F*)gt_.ensure(2 * cnt * 32);
+        launch(k_gen_points<CC>, 2 * cnt, 256, (const F*)f, t, xt, gt);
         tw_max_ = t;
     }
+    const F* xtab(int t) { return xt_.as<F>() + ((size_t)1 << t); }
+    const F* gtab(int t) { return gt_.as<F>() + ((size_t)1 << t); }
     const F* tw(bool inverse, int t) { return (inverse ? tw_inv_.as<F>() : tw_fwd_.as<F>()) + ((size_t)1 << (t - 1)); }
 
     // in-place batched inversion of M elements (zeros stay zero)
@@ -863,13 +868,13 @@ private:
             }
             // pointwise merge with exact division; parents' evaluations go to the next level's buffers (stride 2T)
             {
-                Scope ps(this, "merge_den", pts * 32.0, pts * 1.0);
-                launch(k_den<FB>, wm << t, 256, (const MergeDesc<FB>*)desc, wm, t, tw(false, t), den, d_err_);
+                Scope ps(this, "merge_den", pts * 64.0, pts * 1.0);
+                launch(k_den<FB>, wm << t, 256, (const MergeDesc<FB>*)desc, wm, t, xtab(t), den, d_err_);
             }
             batch_invert(den, wm << t);
             {
-                Scope ps(this, "merge_pointwise", pts * 224.0, pts * 13.0);
-                launch(k_pointwise<CC>, wm << t, 128, (const MergeDesc<FB>*)desc, wm, t, tw(false, t), (const F*)EA[e], (const F*)EB[e],
+                Scope ps(this, "merge_pointwise", pts * 288.0, pts * 11.0);
+                launch(k_pointwise<CC>, wm << t, 128, (const MergeDesc<FB>*)desc, wm, t, xtab(t), gtab(t), (const F*)EA[e], (const F*)EB[e],
                        (const F*)den, merges, nodes, EA[e ^ 1], EB[e ^ 1], 2 * Tn);
             }
             // back to coefficients (unscaled: stored = T * true), compact parent slots

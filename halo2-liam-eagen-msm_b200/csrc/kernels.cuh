@@ -701,6 +701,22 @@ EAGEN_D Fe<FP> eval_point(const Fe<FP>* __restrict__ tw, int t, uint32_t p) {
     return neg(ldg(tw + (kx - half)));
 }
 
+// Evaluation-point tables for every transform size up to 2^tmax: for size T = 2^t, xt[T + p] is the point stored at position p
+// of the bit-reversed forward transform and gt[T + p] = x^3 + b there (y^2 of the curve), so the merge kernels load them
+// instead of decoding the position and spending two products per point.
+template <class CC>
+__global__ void k_gen_points(const Fe<typename CC::Base>* __restrict__ tw_all, int tmax, Fe<typename CC::Base>* __restrict__ xt,
+                             Fe<typename CC::Base>* __restrict__ gt) {
+    typedef typename CC::Base F;
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < 2 || idx >= ((size_t)2 << tmax)) return;
+    int t = 63 - __clzll((unsigned long long)idx);
+    uint32_t p = (uint32_t)(idx - ((size_t)1 << t));
+    Fe<F> x = eval_point(tw_all + ((size_t)1 << (t - 1)), t, p);
+    stg(xt + idx, x);
+    stg(gt + idx, add(mul(sqr(x), x), CC::b()));
+}
+
 // ------------------------------------------------------------------------------------------------
 // K7  merge in the evaluation domain.  Children (a1 + y b1), (a2 + y b2), line l = lz + lx x + ly y,
 // g(x) = x^3 + b:
@@ -709,7 +725,7 @@ EAGEN_D Fe<FP> eval_point(const Fe<FP>* __restrict__ tw, int t, uint32_t p) {
 // then / ((x - alpha)(x - beta)) pointwise (reference: src/regular_functions_utils.rs:266-273,344-357).
 // ------------------------------------------------------------------------------------------------
 template <class FP>
-__global__ void k_den(const MergeDesc<FP>* __restrict__ desc, size_t nmerges, int t, const Fe<FP>* __restrict__ tw,
+__global__ void k_den(const MergeDesc<FP>* __restrict__ desc, size_t nmerges, int t, const Fe<FP>* __restrict__ xt /* x at position p */,
                       Fe<FP>* __restrict__ den, int* err) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (nmerges << t)) return;
@@ -717,7 +733,7 @@ __global__ void k_den(const MergeDesc<FP>* __restrict__ desc, size_t nmerges, in
     uint32_t p = (uint32_t)(g & (((size_t)1 << t) - 1));
     Fe<FP> dv = Fe<FP>::zero();
     if (desc[m].mode == MERGE_GENERIC) {
-        Fe<FP> x = eval_point(tw, t, p);
+        Fe<FP> x = ldg(xt + p);
         dv = mul(sub(x, ldg(&desc[m].alpha)), sub(x, ldg(&desc[m].beta)));
         if (dv.is_zero()) atomicOr(err, KERR_COLLISION);
     }
@@ -728,12 +744,13 @@ __global__ void k_den(const MergeDesc<FP>* __restrict__ desc, size_t nmerges, in
 // (parent m at m*out_stride, out_stride = 2T): positions [0, T) of a 2T-point bit-reversed transform are exactly the
 // T-point domain in bit-reversed order, so the next level only has to add the odd coset (see Engine::run_trees).
 #ifndef EAGEN_PW_MINBLOCKS
-#define EAGEN_PW_MINBLOCKS 8
+#define EAGEN_PW_MINBLOCKS 6
 #endif
 template <class CC>
 __global__ void __launch_bounds__(128, EAGEN_PW_MINBLOCKS)
 k_pointwise(const MergeDesc<typename CC::Base>* __restrict__ desc, size_t nmerges, int t,
-                            const Fe<typename CC::Base>* __restrict__ tw,
+                            const Fe<typename CC::Base>* __restrict__ xt /* x at position p */,
+                            const Fe<typename CC::Base>* __restrict__ gt /* x^3 + b at position p */,
                             const Fe<typename CC::Base>* __restrict__ EA, const Fe<typename CC::Base>* __restrict__ EB,
                             const Fe<typename CC::Base>* __restrict__ dinv, size_t merges_per_tree, size_t nodes_per_tree,
                             Fe<typename CC::Base>* __restrict__ OA, Fe<typename CC::Base>* __restrict__ OB, size_t out_stride) {
@@ -752,8 +769,8 @@ k_pointwise(const MergeDesc<typename CC::Base>* __restrict__ desc, size_t nmerge
         ra = a1; rb = b1;
     } else {
         Fe<F> a2 = ldg(EA + c2), b2 = ldg(EB + c2);
-        Fe<F> x = eval_point(tw, t, p);
-        Fe<F> gx = add(mul(sqr(x), x), CC::b());
+        Fe<F> x = ldg(xt + p);
+        Fe<F> gx = ldg(gt + p);
         // products of the form (u + y v)(u' + y v') = (u u' + v v' g) + y (u v' + v u') with three multiplications for the
         // cross term (Karatsuba): 4 instead of 5 field products each
         if (mode == MERGE_SHORTCUT) {
