@@ -632,6 +632,9 @@ private:
         size_t tiles = (a.total + NTT_TILE - 1) / NTT_TILE;
         for (size_t p = 0; p < plan.size(); ++p) {
             a.s_hi = plan[p].first; a.s_lo = plan[p].second;
+            // w_T^(j 2^(t-1-s)) = w_{2^(s+1)}^j: the last (contiguous) pass only needs the 2^k-point table, which stays in L1
+            a.tw_t = a.s_lo == 0 ? a.s_hi + 1 : t;
+            a.tw = tw(inverse, a.tw_t);
             a.src = (p == 0) ? src : nullptr;
             a.twist = (p == 0) ? twist : nullptr;
             a.dst = (p + 1 == plan.size()) ? dst : nullptr;

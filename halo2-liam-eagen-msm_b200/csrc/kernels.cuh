@@ -545,6 +545,7 @@ struct NttPass {
     int src_len, dst_len;
     int node_max;            // transforms per tree (stride of the tree index)
     int t, s_hi, s_lo;
+    int tw_t;                // log2 of the transform size the twiddle table `tw` belongs to (the contiguous pass uses the compact 2^k table)
 };
 
 EAGEN_D uint32_t insert_zero_bit(uint32_t v, int pos) {
@@ -612,9 +613,9 @@ k_ntt_pass(NttPass<FP> a) {
         const size_t w = (tile << lw) + wl;
         const size_t L = w & (((size_t)1 << a.s_lo) - 1);
         const size_t jl = ((size_t)(E & ((1u << slo) - 1)) << a.s_lo) | L;   // index inside the 2^sgl group (same for all four)
-        const Fe<FP> W0 = ldg(a.tw + (jl << (a.t - 1 - sgl)));
-        const Fe<FP> W1a = ldg(a.tw + (jl << (a.t - 1 - sgh)));
-        const Fe<FP> W1b = ldg(a.tw + ((jl + ((size_t)1 << sgl)) << (a.t - 1 - sgh)));
+        const Fe<FP> W0 = ldg(a.tw + (jl << (a.tw_t - 1 - sgl)));
+        const Fe<FP> W1a = ldg(a.tw + (jl << (a.tw_t - 1 - sgh)));
+        const Fe<FP> W1b = ldg(a.tw + ((jl + ((size_t)1 << sgl)) << (a.tw_t - 1 - sgh)));
         Fe<FP> x0 = s[i0], x1 = s[i0 + d], x2 = s[i0 + 2 * d], x3 = s[i0 + 3 * d];
         if (INVERSE) {   // decimation in time: stage slo (distance d), then stage slo+1 (distance 2d)
             Fe<FP> v1 = mul(x1, W0), v3 = mul(x3, W0);
@@ -642,7 +643,7 @@ k_ntt_pass(NttPass<FP> a) {
             size_t w = (tile << lw) + wl;
             size_t L = w & (((size_t)1 << a.s_lo) - 1);
             size_t j = ((size_t)(E & ((1u << sigma) - 1)) << a.s_lo) | L;
-            Fe<FP> wj = ldg(a.tw + (j << (a.t - 1 - sg)));
+            Fe<FP> wj = ldg(a.tw + (j << (a.tw_t - 1 - sg)));
             Fe<FP> u = s[i0], v = s[i1];
             if (INVERSE) {
                 v = mul(v, wj);
