@@ -43,6 +43,7 @@ ABI_SYMBOLS = [
     "eagen_dev_shard_sums", "eagen_dev_carry_chain", "eagen_dev_trees", "eagen_dev_lhs_witness",
     "eagen_result_device_view", "eagen_synth_inputs", "eagen_dev_synth_inputs",
     "eagen_set_profiling", "eagen_profile_reset", "eagen_profile_json", "eagen_microbench",
+    "eagen_dev_negbase", "eagen_dev_ntt",
 ]
 SELFTEST_SYMBOLS = ["eagen_selftest_field", "eagen_selftest_curve", "eagen_selftest_negbase_params", "eagen_selftest_ntt_plan"]
 
@@ -101,6 +102,8 @@ def lib():
         L.eagen_batch_invert.argtypes = [C.c_void_p, U64P, C.c_size_t]
         L.eagen_eval_function.argtypes = [C.c_void_p, U64P, C.c_size_t, U64P, C.c_size_t, U64P, C.c_size_t, U64P]
         L.eagen_dev_shard_sums.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.eagen_dev_negbase.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        L.eagen_dev_ntt.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
         L.eagen_dev_carry_chain.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint8, C.c_void_p]
         L.eagen_dev_trees.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8, C.c_uint32, C.c_uint32,
                                       C.c_uint32, C.POINTER(C.c_void_p)]
@@ -365,6 +368,16 @@ class Context:
     # ---- device-resident stages (pointers are CUDA device addresses, e.g. torch tensors' data_ptr()) -------------
     def dev_shard_sums(self, d_scalars, d_pts, n, base, d_planes, d_table, d_sums):
         self._chk(lib().eagen_dev_shard_sums(self._h, d_scalars, d_pts, n, C.c_uint8(base), d_planes, d_table, d_sums))
+
+    def dev_negbase(self, d_scalars, n, base, d_planes, d_rows=None):
+        ms = C.c_double()
+        self._chk(lib().eagen_dev_negbase(self._h, d_scalars, n, C.c_uint8(base), d_planes, d_rows, C.byref(ms)))
+        return ms.value
+
+    def dev_ntt(self, d_data, log_n, batch, inverse=False):
+        ms = C.c_double()
+        self._chk(lib().eagen_dev_ntt(self._h, d_data, log_n, batch, int(inverse), C.byref(ms)))
+        return ms.value
 
     def dev_carry_chain(self, d_sums, nparts, base, d_carries):
         self._chk(lib().eagen_dev_carry_chain(self._h, d_sums, nparts, C.c_uint8(base), d_carries))

@@ -184,6 +184,22 @@ int eagen_dev_shard_sums(eagen_ctx* ctx, const void* d_scalars, const void* d_pt
         ctx->eng->shard_sums_dev(d_scalars, d_pts, n, base, d_planes, d_table, d_partial_sums);
     });
 }
+int eagen_dev_negbase(eagen_ctx* ctx, const void* d_scalars, size_t n, uint8_t base, void* d_planes, void* d_rows, double* device_ms) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] {
+        need(base >= 2 && (n == 0 || (d_scalars && d_planes)), "eagen_dev_negbase: bad arguments");
+        double ms = ctx->eng->negbase_dev(d_scalars, n, base, d_planes, d_rows);
+        if (device_ms) *device_ms = ms;
+    });
+}
+int eagen_dev_ntt(eagen_ctx* ctx, void* d_data, uint32_t log_n, size_t batch, int inverse, double* device_ms) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] {
+        need(d_data != nullptr, "eagen_dev_ntt: null buffer");
+        double ms = ctx->eng->ntt_dev(d_data, log_n, batch, inverse);
+        if (device_ms) *device_ms = ms;
+    });
+}
 int eagen_dev_carry_chain(eagen_ctx* ctx, const void* d_partial_sums, int nparts, uint8_t base, void* d_carries) {
     if (!ctx) return EAGEN_E_ARG;
     return guarded(ctx, [&] {

@@ -87,6 +87,8 @@ struct IEngine {
     virtual void eval_host(const uint64_t* a, size_t la, const uint64_t* b, size_t lb, const uint64_t* pts, size_t n, uint64_t* out) = 0;
     virtual void shard_sums_dev(const void* d_scalars, const void* d_pts, size_t n, uint8_t base, void* d_planes, void* d_table, void* d_sums) = 0;
     virtual void carry_chain_dev(const void* d_sums, int nparts, uint8_t base, void* d_carries) = 0;
+    virtual double negbase_dev(const void* d_scalars, size_t n, uint8_t base, void* d_planes, void* d_rows) = 0;
+    virtual double ntt_dev(void* d_data, uint32_t log_n, size_t batch, int inverse) = 0;
     virtual double microbench(int which) = 0;
     virtual void set_profiling(bool on) = 0;
     virtual std::string profile_json() = 0;
@@ -162,7 +164,26 @@ inline NegbaseParams make_negbase_params(uint8_t base) {
     std::memcpy(p.K, K.w, 32);
     std::memcpy(p.bd, pw.w, 32);
     p.chunk_digits = 0; p.chunk = 1;
-    while ((uint64_t)p.chunk * base < (1ull << 32)) { p.chunk *= base; ++p.chunk_digits; }
+    while ((uint64_t)p.chunk * base <= (1u << 15)) { p.chunk *= base; ++p.chunk_digits; }
+    // multiply-shift reciprocals, exact for 31-bit dividends: M = ceil(2^k / dv), k = 31 + ceil(log2 dv)
+    auto magic = [](uint32_t dv, uint32_t& m, uint32_t& k) {
+        uint32_t s = 0;
+        while ((1u << s) < dv) ++s;
+        k = 31 + s;
+        m = (uint32_t)((((uint64_t)1 << k) + dv - 1) / dv);
+    };
+    magic(p.chunk, p.chunk_magic, p.chunk_shift);
+    magic(base, p.base_magic, p.base_shift);
+    // before step s the running quotient is < base^(d - s*chunk_digits): highest possibly non-zero 16-bit half-limb
+    std::memset(p.tops, 0, sizeof p.tops);
+    for (uint32_t s = 0; s * p.chunk_digits < p.d && s < 32; ++s) {
+        HostU256 bound = HostU256::zero();
+        bound.w[0] = 1;
+        for (uint32_t i = 0; i < p.d - s * p.chunk_digits; ++i) bound.mul_small_add(base, 0);
+        int top = 15;
+        while (top > 0 && ((bound.w[top / 2] >> (16 * (top & 1))) & 0xffffu) == 0) --top;
+        p.tops[s] = (uint8_t)top;
+    }
     return p;
 }
 
@@ -296,6 +317,35 @@ public:
         NegbaseParams prm = make_negbase_params<FS>(base);
         run_shard_sums((const Fe<FS>*)d_scalars, (const F*)d_pts, n, prm, (uint8_t*)d_planes, nullptr, (Aff*)d_table, (Prj*)d_sums);
         sync_check();
+    }
+    // stand-alone K1 on device buffers; returns the device milliseconds (CUDA events on the launching stream)
+    double negbase_dev(const void* d_scalars, size_t n, uint8_t base, void* d_planes, void* d_rows) override {
+        use();
+        NegbaseParams prm = make_negbase_params<FS>(base);
+        EAGEN_CUDA(cudaEventRecord(ev0_, st_));
+        if (n) run_negbase((const Fe<FS>*)d_scalars, n, prm, (uint8_t*)d_planes, (uint8_t*)d_rows);
+        EAGEN_CUDA(cudaEventRecord(ev1_, st_));
+        sync_check();
+        float ms = 0; EAGEN_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+        return ms;
+    }
+    // stand-alone K6: `batch` transforms of 2^log_n elements in place (forward: natural -> bit-reversed, inverse: bit-reversed ->
+    // natural, unscaled); returns device milliseconds
+    double ntt_dev(void* d_data, uint32_t log_n, size_t batch, int inverse) override {
+        use();
+        if (log_n == 0 || batch == 0) return 0.0;
+        if (log_n > FB::S) throw StatusError{EAGEN_E_NTT_TOO_LARGE, "log_n exceeds the field's two-adicity"};
+        ensure_twiddles((int)log_n);
+        int* cnt = (int*)tops_.ensure(sizeof(int));
+        int one_batch = (int)batch;
+        EAGEN_CUDA(cudaMemcpyAsync(cnt, &one_batch, sizeof(int), cudaMemcpyHostToDevice, st_));
+        EAGEN_CUDA(cudaStreamSynchronize(st_));
+        EAGEN_CUDA(cudaEventRecord(ev0_, st_));
+        ntt(inverse != 0, (F*)d_data, nullptr, 0, 0, nullptr, 0, 0, (int)log_n, batch, cnt, (int)batch);
+        EAGEN_CUDA(cudaEventRecord(ev1_, st_));
+        sync_check();
+        float ms = 0; EAGEN_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+        return ms;
     }
     void carry_chain_dev(const void* d_sums, int nparts, uint8_t base, void* d_carries) override {
         use();

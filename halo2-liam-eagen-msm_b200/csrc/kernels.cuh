@@ -111,7 +111,10 @@ struct NegbaseParams {
     uint32_t sq[8];      // isqrt(order)+2 (canonical limbs)
     uint32_t K[8];       // offset constant
     uint32_t bd[8];      // b^d
-    uint32_t base, d, chunk_digits, chunk;  // chunk = base^chunk_digits < 2^32
+    uint32_t base, d, chunk_digits, chunk;  // chunk = base^chunk_digits <= 2^15, so (rem << 16 | half-limb) fits 31 bits
+    uint32_t chunk_magic, chunk_shift;      // x / chunk == (x * chunk_magic) >> chunk_shift  for x < 2^31
+    uint32_t base_magic, base_shift;        // x / base  == (x * base_magic)  >> base_shift   for x < 2^31
+    uint8_t tops[32];                       // tops[s] = index of the highest possibly non-zero 16-bit half-limb before step s
 };
 
 EAGEN_HD bool lt8(const uint32_t* a, const uint32_t* b) {
@@ -121,6 +124,10 @@ EAGEN_HD bool lt8(const uint32_t* a, const uint32_t* b) {
     return false;
 }
 
+// One thread per scalar: two 128-bit loads, Montgomery -> canonical, + K, then short division of 16-bit half-limbs by
+// base^c <= 2^15 with multiply-shift reciprocals (no hardware divide: a 64-bit `div` costs ~100 instructions and made the
+// first version of this kernel integer-bound at 10 % of HBM bandwidth), digits peeled from each chunk the same way.
+// Plane stores are coalesced across the warp (32 consecutive bytes per digit position).
 template <class FS>
 __global__ void k_negbase(const Fe<FS>* __restrict__ scalars, size_t n, NegbaseParams prm, uint8_t* __restrict__ planes /* d x n */,
                           uint8_t* __restrict__ rows /* n x d or null */, int* err) {
@@ -133,22 +140,28 @@ __global__ void k_negbase(const Fe<FS>* __restrict__ scalars, size_t n, NegbaseP
 #pragma unroll
     for (int i = 0; i < 8; ++i) { c += (uint64_t)x.v[i] + prm.K[i]; y[i] = (uint32_t)c; c >>= 32; }
     if (!lt8(y, prm.bd)) { atomicOr(err, KERR_DIGITS); return; }
+    uint32_t h[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { h[2 * i] = y[i] & 0xffffu; h[2 * i + 1] = y[i] >> 16; }
     const uint32_t d = prm.d, base = prm.base;
-    int top = 7;
-    while (top > 0 && y[top] == 0) --top;
     uint32_t i = 0;
-    while (i < d) {
-        uint64_t rem = 0;
-        for (int l = top; l >= 0; --l) {
-            uint64_t cur = (rem << 32) | y[l];
-            y[l] = (uint32_t)(cur / prm.chunk);
-            rem = cur % prm.chunk;
+    for (int step = 0; i < d; ++step) {
+        const int top = prm.tops[step];   // host-computed bound, uniform across the grid: h[] stays in registers
+        uint32_t rem = 0;
+#pragma unroll
+        for (int l = 15; l >= 0; --l) {
+            if (l <= top) {
+                uint32_t cur = (rem << 16) | h[l];
+                uint32_t q = (uint32_t)(((uint64_t)cur * prm.chunk_magic) >> prm.chunk_shift);
+                rem = cur - q * prm.chunk;
+                h[l] = q;
+            }
         }
-        while (top > 0 && y[top] == 0) --top;
-        uint32_t r = (uint32_t)rem;
+        uint32_t r = rem;
         for (uint32_t k = 0; k < prm.chunk_digits && i < d; ++k, ++i) {
-            uint32_t e = r % base;
-            r /= base;
+            uint32_t q = (uint32_t)(((uint64_t)r * prm.base_magic) >> prm.base_shift);
+            uint32_t e = r - q * base;
+            r = q;
             uint32_t dg = (i & 1) ? (base - 1 - e) : e;
             uint32_t pos = d - 1 - i;  // MSD first
             planes[(size_t)pos * n + j] = (uint8_t)dg;

@@ -156,6 +156,11 @@ int eagen_dev_synth_inputs(eagen_ctx* ctx, uint64_t seed, size_t n, void* d_scal
  * digit sums of this shard as homogeneous projective points (d x 96 B, X|Y|Z).                              */
 int eagen_dev_shard_sums(eagen_ctx* ctx, const void* d_scalars, const void* d_pts, size_t n, uint8_t base,
                          void* d_planes, void* d_table, void* d_partial_sums);
+/* stand-alone kernels on device buffers (BASELINE config 5 sweeps): K1 digits of n scalars into d x n planes (and n x d rows
+ * when d_rows != NULL); K6 `batch` in-place transforms of 2^log_n elements (forward: natural -> bit-reversed order, inverse:
+ * bit-reversed -> natural, unscaled).  device_ms (may be NULL) receives the CUDA-event time on the launching stream. */
+int eagen_dev_negbase(eagen_ctx* ctx, const void* d_scalars, size_t n, uint8_t base, void* d_planes, void* d_rows, double* device_ms);
+int eagen_dev_ntt(eagen_ctx* ctx, void* d_data, uint32_t log_n, size_t batch, int inverse, double* device_ms);
 /* stage B: carry chain over `nparts` gathered partial sums (nparts x d projective) -> d affine carries      */
 int eagen_dev_carry_chain(eagen_ctx* ctx, const void* d_partial_sums, int nparts, uint8_t base, void* d_carries);
 /* stage C: divisor witnesses for the digit positions [pos_begin, pos_end) of the MSD-first iteration order,

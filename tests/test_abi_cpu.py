@@ -107,7 +107,7 @@ def test_negbase_constants(eagen):
             d = pyref.num_digits(cv, base)
             assert prm["d"] == d and prm["sq"] == pyref.isqrt(cv.q) + 2
             assert prm["K"] == sum((base - 1) * base ** i for i in range(1, d, 2)) and prm["bd"] == base ** d
-            assert prm["chunk"] == base ** prm["chunk_digits"] < 2 ** 32 <= prm["chunk"] * base
+            assert prm["chunk"] == base ** prm["chunk_digits"] <= 2 ** 15 < prm["chunk"] * base
             rng = pyref.SplitMix64(base)
             for _ in range(50):
                 x = rng.next_bits(2) % prm["sq"]
