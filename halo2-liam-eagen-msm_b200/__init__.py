@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
     "eagen_dev_shard_sums", "eagen_dev_carry_chain", "eagen_dev_trees", "eagen_dev_lhs_witness",
     "eagen_result_device_view", "eagen_synth_inputs", "eagen_dev_synth_inputs",
     "eagen_set_profiling", "eagen_profile_reset", "eagen_profile_json", "eagen_microbench",
-    "eagen_dev_negbase", "eagen_dev_ntt",
+    "eagen_dev_negbase", "eagen_dev_ntt", "eagen_lhs_witness_stream", "eagen_lhs_witness_stream_layout",
 ]
 SELFTEST_SYMBOLS = ["eagen_selftest_field", "eagen_selftest_curve", "eagen_selftest_negbase_params", "eagen_selftest_ntt_plan"]
 
@@ -78,6 +78,9 @@ def lib():
         L.eagen_negbase_decompose.argtypes = [C.c_void_p, U64P, C.c_size_t, C.c_uint8, U8P]
         L.eagen_precompute_multiplicities.argtypes = [C.c_void_p, U64P, C.c_size_t, C.c_uint8, U64P]
         L.eagen_lhs_witness.argtypes = [C.c_void_p, U64P, U64P, C.c_size_t, C.c_uint8, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.eagen_lhs_witness_stream_layout.argtypes = [C.c_int, C.c_size_t, C.c_uint8, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.eagen_lhs_witness_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8, C.c_uint32, C.c_void_p, C.c_size_t,
+                                               C.POINTER(C.c_void_p)]
         L.eagen_dev_lhs_witness.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8, C.c_uint32, C.POINTER(C.c_void_p)]
         L.eagen_divisor_witness.argtypes = [C.c_void_p, U64P, C.c_size_t, C.c_uint32, U64P, C.POINTER(C.c_void_p)]
         L.eagen_result_num_digits.restype = C.c_uint32
@@ -313,6 +316,19 @@ class Context:
         else:
             self._chk(lib().eagen_lhs_witness(self._h, C.cast(C.c_void_p(scalars_ptr), U64P), C.cast(C.c_void_p(pts_ptr), U64P), n,
                                               C.c_uint8(base), flags, C.byref(h)))
+        return WitnessResult(self, h, n)
+
+    def stream_layout(self, n, base):
+        """(a_stride, b_stride, total_bytes) of the streamed result layout"""
+        a, b, t = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        self._chk(lib().eagen_lhs_witness_stream_layout(self.curve, n, C.c_uint8(base), C.byref(a), C.byref(b), C.byref(t)))
+        return a.value, b.value, t.value
+
+    def compute_lhs_witness_stream(self, scalars_ptr, pts_ptr, n, base, out_ptr, out_bytes, flags=CANONICAL):
+        """host pointers in, functions streamed into the host buffer at out_ptr (see eagen_lhs_witness_stream)"""
+        h = C.c_void_p()
+        self._chk(lib().eagen_lhs_witness_stream(self._h, C.c_void_p(scalars_ptr), C.c_void_p(pts_ptr), n, C.c_uint8(base), flags,
+                                                 C.c_void_p(out_ptr), out_bytes, C.byref(h)))
         return WitnessResult(self, h, n)
 
     def compute_divisor_witness_partial(self, pts, flags=CANONICAL):

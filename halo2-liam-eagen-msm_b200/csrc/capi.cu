@@ -159,6 +159,23 @@ int eagen_lhs_witness(eagen_ctx* ctx, const uint64_t* scalars, const uint64_t* p
     });
 }
 
+int eagen_lhs_witness_stream_layout(int curve, size_t n, uint8_t base, size_t* a_stride, size_t* b_stride, size_t* total_bytes) {
+    return guarded(nullptr, [&] {
+        need(a_stride && b_stride && base >= 2, "eagen_lhs_witness_stream_layout: bad arguments");
+        stream_slot_elems(n, base, a_stride, b_stride);
+        if (total_bytes) *total_bytes = (size_t)digits_of_curve(curve, base) * (*a_stride + *b_stride) * 32;
+    });
+}
+int eagen_lhs_witness_stream(eagen_ctx* ctx, const uint64_t* scalars, const uint64_t* pts, size_t n, uint8_t base, uint32_t flags,
+                             void* out, size_t out_bytes, eagen_result** res) {
+    if (!ctx || !res) return EAGEN_E_ARG;
+    *res = nullptr;
+    return guarded(ctx, [&] {
+        need(base >= 2 && out && (n == 0 || (scalars && pts)), "eagen_lhs_witness_stream: bad arguments");
+        *res = new eagen_result{ctx->eng->lhs_stream_host(scalars, pts, n, base, flags, out, out_bytes)};
+    });
+}
+
 int eagen_dev_lhs_witness(eagen_ctx* ctx, const void* d_scalars, const void* d_pts, size_t n, uint8_t base, uint32_t flags, eagen_result** out) {
     if (!ctx || !out) return EAGEN_E_ARG;
     *out = nullptr;

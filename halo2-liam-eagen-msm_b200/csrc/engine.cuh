@@ -10,6 +10,7 @@
 #pragma once
 #include <algorithm>
 #include <memory>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -53,11 +54,47 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     ~DevBuf() { release(); }
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; } return *this; }
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+// Result buffers are recycled through a pool shared by the context and its results: cudaFree of a ~2 GB buffer was measured
+// at up to 0.5 s on the B200 boxes (and is device-synchronising), which would dominate a 0.4 s witness call.
+struct BufPool {
+    std::mutex m;
+    std::vector<DevBuf> bufs;
+    DevBuf take(size_t bytes) {
+        std::lock_guard<std::mutex> lk(m);
+        int best = -1;
+        for (size_t i = 0; i < bufs.size(); ++i)
+            if (bufs[i].cap >= bytes && (best < 0 || bufs[i].cap < bufs[(size_t)best].cap)) best = (int)i;
+        DevBuf b;
+        if (best >= 0) { b = std::move(bufs[(size_t)best]); bufs.erase(bufs.begin() + best); }
+        else {
+            if (bufs.size() >= 8) bufs.erase(bufs.begin());  // bounded: drop the oldest (frees it)
+            b.ensure(bytes);
+        }
+        return b;
+    }
+    void give(DevBuf&& b) {
+        if (!b.p) return;
+        std::lock_guard<std::mutex> lk(m);
+        bufs.push_back(std::move(b));
+    }
 };
 
 // ---- result handle -------------------------------------------------------------------------------------
 struct ResultImpl {
+    std::shared_ptr<BufPool> pool;       // buffers go back to the owning context's pool when the result is freed
+    ~ResultImpl() { if (pool) { pool->give(std::move(A)); pool->give(std::move(B)); pool->give(std::move(digits)); } }
+    void alloc(DevBuf& b, size_t bytes) {
+        if (b.cap >= bytes) return;
+        if (pool) { pool->give(std::move(b)); b = pool->take(bytes); } else b.ensure(bytes);
+    }
     int device = 0;
     uint32_t d = 0;
     size_t n = 0;
@@ -72,8 +109,24 @@ struct ResultImpl {
     double device_ms = 0;
 };
 
+// host destination of a streamed result: function k at out + k*(a_stride + b_stride)*32 (a first, then b)
+struct StreamOut {
+    uint8_t* out = nullptr;
+    size_t a_stride = 0, b_stride = 0;  // elements
+};
+
+// slot sizes of the streamed layout from an upper bound of the list length (n + base + 1 points per digit position)
+inline void stream_slot_elems(size_t n, uint8_t base, size_t* a_stride, size_t* b_stride) {
+    size_t nmax = n + base + 1, lc = (nmax + 1) / 2;
+    int L = 0;
+    while (((size_t)1 << L) < lc) ++L;
+    *a_stride = ((size_t)1 << L) + 1;
+    *b_stride = std::max<size_t>((size_t)1 << L, 1);
+}
+
 struct IEngine {
     virtual ~IEngine() {}
+    virtual ResultImpl* lhs_stream_host(const uint64_t* scalars, const uint64_t* pts, size_t n, uint8_t base, uint32_t flags, void* out, size_t out_bytes) = 0;
     virtual int device() const = 0;
     virtual uint64_t launches() const = 0;
     virtual void negbase_host(const uint64_t* scalars, size_t n, uint8_t base, uint8_t* digits) = 0;
@@ -211,6 +264,7 @@ public:
     explicit Engine(int dev) : dev_(dev) {
         EAGEN_CUDA(cudaSetDevice(dev_));
         EAGEN_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+        EAGEN_CUDA(cudaStreamCreateWithFlags(&cst_, cudaStreamNonBlocking));
         EAGEN_CUDA(cudaMalloc(&d_err_, sizeof(int)));
         EAGEN_CUDA(cudaMemsetAsync(d_err_, 0, sizeof(int), st_));
         EAGEN_CUDA(cudaEventCreate(&ev0_));
@@ -225,6 +279,7 @@ public:
         cudaStreamSynchronize(st_);
         cudaFree(d_err_); cudaFree(d_one_);
         cudaEventDestroy(ev0_); cudaEventDestroy(ev1_);
+        cudaStreamDestroy(cst_);
         cudaStreamDestroy(st_);
     }
     int device() const override { return dev_; }
@@ -285,7 +340,29 @@ public:
         return lhs_dev(ds, dp, n, base, flags);
     }
 
+    // compute_lhs_witness from host buffers with the functions copied into `out` while later digit positions are still being
+    // computed (the D2H of 1.5 GB at 2^20 otherwise adds ~25 % to the call)
+    ResultImpl* lhs_stream_host(const uint64_t* scalars, const uint64_t* pts, size_t n, uint8_t base, uint32_t flags, void* out, size_t out_bytes) override {
+        use();
+        NegbaseParams prm = make_negbase_params<FS>(base);
+        StreamOut so;
+        so.out = (uint8_t*)out;
+        stream_slot_elems(n, base, &so.a_stride, &so.b_stride);
+        if (out_bytes < (size_t)prm.d * (so.a_stride + so.b_stride) * 32) throw StatusError{EAGEN_E_LEN, "streamed output buffer too small"};
+        Fe<FS>* ds = (Fe<FS>*)in_scalars_.ensure(std::max<size_t>(n, 1) * 32);
+        F* dp = (F*)in_points_.ensure(std::max<size_t>(n, 1) * 96);
+        if (n) {
+            EAGEN_CUDA(cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, st_));
+            EAGEN_CUDA(cudaMemcpyAsync(dp, pts, n * 96, cudaMemcpyHostToDevice, st_));
+        }
+        return lhs_dev_impl(ds, dp, n, base, flags, &so);
+    }
+
     ResultImpl* lhs_dev(const void* d_scalars, const void* d_pts, size_t n, uint8_t base, uint32_t flags) override {
+        return lhs_dev_impl(d_scalars, d_pts, n, base, flags, nullptr);
+    }
+
+    ResultImpl* lhs_dev_impl(const void* d_scalars, const void* d_pts, size_t n, uint8_t base, uint32_t flags, const StreamOut* so) {
         use();
         NegbaseParams prm = make_negbase_params<FS>(base);
         const uint32_t d = prm.d;
@@ -297,13 +374,13 @@ public:
         Aff* carries = (Aff*)carries_.ensure((size_t)d * sizeof(Aff));
         uint8_t* rows = nullptr;
         std::unique_ptr<ResultImpl> res(new ResultImpl());
-        res->device = dev_; res->d = d; res->n = n;
-        if (flags & EAGEN_KEEP_DIGITS) { rows = (uint8_t*)res->digits.ensure(nn * d); res->has_digits = true; }
+        res->device = dev_; res->pool = pool_; res->d = d; res->n = n;
+        if (flags & EAGEN_KEEP_DIGITS) { res->alloc(res->digits, nn * d); rows = (uint8_t*)res->digits.p; res->has_digits = true; }
         run_shard_sums((const Fe<FS>*)d_scalars, (const F*)d_pts, n, prm, planes, rows, tab, sums);
         run_carry_chain(sums, 1, d, base, carries);
         res->carries.assign((size_t)d * 8, 0);
         EAGEN_CUDA(cudaMemcpyAsync(res->carries.data(), carries, (size_t)d * 64, cudaMemcpyDeviceToHost, st_));
-        if (!(flags & EAGEN_NO_FUNCTIONS)) run_position_trees(planes, tab, carries, n, base, d, 0, d, flags, res.get());
+        if (!(flags & EAGEN_NO_FUNCTIONS)) run_position_trees(planes, tab, carries, n, base, d, 0, d, flags, res.get(), so);
         EAGEN_CUDA(cudaEventRecord(ev1_, st_));
         sync_check();
         std::memcpy(res->carry, &res->carries[(size_t)(d - 1) * 8], 64);
@@ -359,7 +436,7 @@ public:
         NegbaseParams prm = make_negbase_params<FS>(base);
         if (pos_begin > pos_end || pos_end > prm.d) throw StatusError{EAGEN_E_ARG, "digit position range out of bounds"};
         std::unique_ptr<ResultImpl> res(new ResultImpl());
-        res->device = dev_; res->d = prm.d; res->n = n;
+        res->device = dev_; res->pool = pool_; res->d = prm.d; res->n = n;
         EAGEN_CUDA(cudaEventRecord(ev0_, st_));
         res->carries.assign((size_t)prm.d * 8, 0);
         EAGEN_CUDA(cudaMemcpyAsync(res->carries.data(), d_carries, (size_t)prm.d * 64, cudaMemcpyDeviceToHost, st_));
@@ -415,12 +492,12 @@ public:
     ResultImpl* divisor_host(const uint64_t* pts, size_t n, uint32_t flags, uint64_t* out_point) override {
         use();
         std::unique_ptr<ResultImpl> res(new ResultImpl());
-        res->device = dev_; res->n = n;
+        res->device = dev_; res->pool = pool_; res->n = n;
         if (n == 0) {  // reference: :455 -> (from_const(1), identity)
             res->nf = 1; res->a_stride = 1; res->b_stride = 1;
             F one = F::one();
-            EAGEN_CUDA(cudaMemcpyAsync(res->A.ensure(32), &one, 32, cudaMemcpyHostToDevice, st_));
-            res->B.ensure(32);
+            res->alloc(res->A, 32); res->alloc(res->B, 32);
+            EAGEN_CUDA(cudaMemcpyAsync(res->A.p, &one, 32, cudaMemcpyHostToDevice, st_));
             res->la = {1}; res->lb = {0};
             if (out_point) std::memset(out_point, 0, 64);
             sync_check();
@@ -573,7 +650,8 @@ private:
     }
 
     int dev_;
-    cudaStream_t st_ = nullptr;
+    std::shared_ptr<BufPool> pool_ = std::make_shared<BufPool>();
+    cudaStream_t st_ = nullptr, cst_ = nullptr;  // compute stream, copy stream (streamed results)
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     int* d_err_ = nullptr;
     int* d_one_ = nullptr;
@@ -742,7 +820,7 @@ private:
 
     // divisor witnesses for iteration positions [pos_begin, pos_end); function index k = d-1-pos (ret.reverse(), :132)
     void run_position_trees(const uint8_t* planes, const Aff* tab, const Aff* carries, size_t n, uint8_t base, uint32_t d,
-                            uint32_t pos_begin, uint32_t pos_end, uint32_t flags, ResultImpl* res) {
+                            uint32_t pos_begin, uint32_t pos_end, uint32_t flags, ResultImpl* res, const StreamOut* so = nullptr) {
         const uint32_t npos = pos_end - pos_begin;
         if (npos == 0) return;
         int chunks = (int)std::max<size_t>(1, (n + CHUNK_PTS - 1) / CHUNK_PTS);
@@ -763,8 +841,8 @@ private:
         res->nf = npos;
         res->a_stride = ((size_t)1 << Lmax) + 1;
         res->b_stride = std::max<size_t>((size_t)1 << Lmax, 1);
-        res->A.ensure(res->nf * res->a_stride * 32);
-        res->B.ensure(res->nf * res->b_stride * 32);
+        res->alloc(res->A, res->nf * res->a_stride * 32);
+        res->alloc(res->B, res->nf * res->b_stride * 32);
         res->la.assign(npos, 0); res->lb.assign(npos, 0);
         // group positions so that one group's working set fits the memory budget
         size_t free_b = 0, total_b = 0;
@@ -772,6 +850,7 @@ private:
         size_t per_tree = tree_bytes(nmax);
         size_t budget = (size_t)((double)(free_b + pooled_bytes()) * 0.80);
         uint32_t group = (uint32_t)std::max<size_t>(1, std::min<size_t>(npos, budget / std::max<size_t>(per_tree, 1)));
+        if (so) group = std::min<uint32_t>(group, (npos + 6) / 7);  // streamed output: ~7 groups so that only 1/7 of the D2H is exposed
         int* tree_of_pos = (int*)tree_of_pos_.ensure((size_t)d * sizeof(int));
         std::vector<Aff> roots(npos);
         for (uint32_t g0 = pos_begin; g0 < pos_end; g0 += group) {
@@ -789,7 +868,15 @@ private:
             // result slot of position p is k = d-1-p; within this result handle slots are relative to the range:
             // slot = (pos_end-1-p), so slot 0 is the highest position of the range (= lowest k)
             run_trees(T, nmax, cnts, flags, res, /*first slot*/ pos_end - g1, /*reverse*/ -1, roots.data() + (g0 - pos_begin));
+            if (so) {  // run_trees has synchronised the compute stream: this group's functions are final, copy them on the copy stream
+                for (size_t slot = pos_end - g1; slot < (size_t)(pos_end - g0); ++slot) {
+                    uint8_t* dst = so->out + slot * (so->a_stride + so->b_stride) * 32;
+                    if (res->la[slot]) EAGEN_CUDA(cudaMemcpyAsync(dst, res->A.as<F>() + slot * res->a_stride, (size_t)res->la[slot] * 32, cudaMemcpyDeviceToHost, cst_));
+                    if (res->lb[slot]) EAGEN_CUDA(cudaMemcpyAsync(dst + so->a_stride * 32, res->B.as<F>() + slot * res->b_stride, (size_t)res->lb[slot] * 32, cudaMemcpyDeviceToHost, cst_));
+                }
+            }
         }
+        if (so) EAGEN_CUDA(cudaStreamSynchronize(cst_));
         sync_check();
         for (uint32_t i = 0; i < npos; ++i)
             if (!roots[i].is_identity()) throw StatusError{EAGEN_E_SUM_NONZERO, "internal: a digit position's points do not sum to the identity"};
@@ -816,7 +903,7 @@ private:
         if (res->nf == 0) {  // stand-alone call: size the result here
             int Lm = ceil_log2((nmax + 1) / 2);
             res->nf = nt; res->a_stride = ((size_t)1 << Lm) + 1; res->b_stride = std::max<size_t>((size_t)1 << Lm, 1);
-            res->A.ensure(res->nf * res->a_stride * 32); res->B.ensure(res->nf * res->b_stride * 32);
+            res->alloc(res->A, res->nf * res->a_stride * 32); res->alloc(res->B, res->nf * res->b_stride * 32);
             res->la.assign(nt, 0); res->lb.assign(nt, 0);
         }
         const size_t lc_max = (nmax + 1) / 2;

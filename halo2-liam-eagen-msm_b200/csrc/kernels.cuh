@@ -231,7 +231,7 @@ __global__ void k_jac_to_affine(const Fe<FP>* __restrict__ jac, const Fe<FP>* __
 constexpr int SUMS_THREADS = 128;
 
 template <class CC>
-__global__ void __launch_bounds__(SUMS_THREADS)
+__global__ void __launch_bounds__(SUMS_THREADS, 5)
 k_digit_sums(const uint8_t* __restrict__ planes, const Affine<typename CC::Base>* __restrict__ table, size_t n, uint32_t base,
              int per_thread, Proj<typename CC::Base>* __restrict__ partials /* d x chunks */) {
     typedef typename CC::Base F;

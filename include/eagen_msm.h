@@ -100,6 +100,15 @@ int eagen_precompute_multiplicities(eagen_ctx* ctx, const uint64_t* pts, size_t 
 int eagen_lhs_witness(eagen_ctx* ctx, const uint64_t* scalars, const uint64_t* pts, size_t n, uint8_t base,
                       uint32_t flags, eagen_result** out);
 
+/* compute_lhs_witness with the functions STREAMED into a caller buffer (pinned host memory recommended) while later digit
+ * positions are still being computed, so the device-to-host copy of the result (1.5 GB at 2^20) overlaps the kernels.
+ * Layout: function k lives in slot k of (a_stride + b_stride) elements: a_k at out + k*(a_stride+b_stride)*32, b_k right after
+ * the a_stride elements; valid lengths come from eagen_result_poly_len.  eagen_lhs_witness_stream_layout gives the strides
+ * and the buffer size for (n, base) before the call.                                                                */
+int eagen_lhs_witness_stream_layout(int curve, size_t n, uint8_t base, size_t* a_stride, size_t* b_stride, size_t* total_bytes);
+int eagen_lhs_witness_stream(eagen_ctx* ctx, const uint64_t* scalars, const uint64_t* pts, size_t n, uint8_t base,
+                             uint32_t flags, void* out, size_t out_bytes, eagen_result** res);
+
 /* compute_divisor_witness / compute_divisor_witness_partial   src/regular_functions_utils.rs:453-480
  * pts: n Jacobian points.  out_point (may be NULL): affine output point (-sum), 64 bytes.                   */
 int eagen_divisor_witness(eagen_ctx* ctx, const uint64_t* pts, size_t n, uint32_t flags, uint64_t* out_point,

@@ -281,3 +281,24 @@ def test_lhs_errors(gpu_ctx, oracle, eagen):
     # the context stays usable after an error
     r = ctx.compute_lhs_witness(oracle.pack_felts(sc, cv.q), P, 5)
     assert r.num_functions == 56
+
+
+def test_lhs_witness_streamed_output(gpu_ctx, oracle, eagen):
+    """eagen_lhs_witness_stream: same functions as the handle-based call, laid out in fixed slots of the caller's buffer"""
+    ctx = gpu_ctx("pallas")
+    n = 3000
+    S, P = ctx.synth_inputs(7, n)
+    ref = ctx.compute_lhs_witness(S, P, 5)
+    a_s, b_s, total = ctx.stream_layout(n, 5)
+    assert total == ref.d * (a_s + b_s) * 32
+    buf = np.zeros(total // 8, dtype=np.uint64)
+    r = ctx.compute_lhs_witness_stream(S.ctypes.data, P.ctypes.data, n, 5, buf.ctypes.data, total)
+    assert (r.carry == ref.carry).all() and r.num_functions == ref.num_functions
+    slots = buf.reshape(ref.d, a_s + b_s, 4)
+    for k in range(ref.d):
+        fa, fb = ref.poly(k, 0), ref.poly(k, 1)
+        assert len(r.poly(k, 0)) == len(fa) and len(r.poly(k, 1)) == len(fb)
+        assert (slots[k, :len(fa)] == fa).all() and (slots[k, a_s:a_s + len(fb)] == fb).all()
+    with pytest.raises(eagen.EagenError) as e:
+        ctx.compute_lhs_witness_stream(S.ctypes.data, P.ctypes.data, n, 5, buf.ctypes.data, total - 32)
+    assert e.value.status == eagen.E_LEN
