@@ -44,6 +44,7 @@ ABI_SYMBOLS = [
     "eagen_result_device_view", "eagen_synth_inputs", "eagen_dev_synth_inputs",
     "eagen_set_profiling", "eagen_profile_reset", "eagen_profile_json", "eagen_microbench",
     "eagen_dev_negbase", "eagen_dev_ntt", "eagen_lhs_witness_stream", "eagen_lhs_witness_stream_layout",
+    "eagen_table_entry_by_id",
 ]
 SELFTEST_SYMBOLS = ["eagen_selftest_field", "eagen_selftest_curve", "eagen_selftest_negbase_params", "eagen_selftest_ntt_plan"]
 
@@ -146,6 +147,16 @@ def num_digits(curve, base):
 def fft_precomp(curve, which, exp):
     out = np.zeros(4, dtype=np.uint64)
     rc = lib().eagen_fft_precomp(curve, which, C.c_uint64(exp), _p64(out))
+    if rc:
+        raise EagenError(rc, lib().eagen_status_string(rc).decode())
+    return out
+
+
+def table_entry_by_id(curve, base, idx):
+    """reference: src/negbase_utils.rs:58-77 over the curve's base field"""
+    out = np.zeros(4, dtype=np.uint64)
+    lib().eagen_table_entry_by_id.argtypes = [C.c_int, C.c_uint8, C.c_size_t, U64P]
+    rc = lib().eagen_table_entry_by_id(curve, C.c_uint8(base), idx, _p64(out))
     if rc:
         raise EagenError(rc, lib().eagen_status_string(rc).decode())
     return out

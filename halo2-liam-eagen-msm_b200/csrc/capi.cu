@@ -51,6 +51,20 @@ template <class FP> void precomp(int which, uint64_t e, uint64_t* out) {
     else { r = Fe<FP>::one(); for (uint64_t i = 0; i < e; ++i) r = mul(r, Fe<FP>::two_inv()); }
     std::memcpy(out, r.v, 32);
 }
+// table_entry_by_id restated on the host with the kernels' field code (reference: src/negbase_utils.rs:58-77)
+template <class FP> void table_entry(uint8_t base, size_t id, uint64_t* out) {
+    Fe<FP> acc = Fe<FP>::zero();
+    if (id != 0) {
+        Fe<FP> b = neg(from_u32<FP>(base));
+        int l = 0;
+        while ((id >> l) != 0) ++l;
+        for (int i = l - 1; i >= 0; --i) {
+            if ((id >> i) & 1) acc = add(acc, Fe<FP>::one());
+            acc = mul(acc, b);
+        }
+    }
+    std::memcpy(out, acc.v, 32);
+}
 }  // namespace
 
 extern "C" {
@@ -126,6 +140,18 @@ int eagen_profile_json(eagen_ctx* ctx, char* buf, size_t cap) {
 
 int eagen_num_digits(int curve, uint8_t base, uint32_t* d) {
     return guarded(nullptr, [&] { need(d && base >= 2, "eagen_num_digits: null output or base < 2"); *d = digits_of_curve(curve, base); });
+}
+
+int eagen_table_entry_by_id(int curve, uint8_t base, size_t id, uint64_t* out) {
+    return guarded(nullptr, [&] {
+        need(out != nullptr, "eagen_table_entry_by_id: null output");
+        switch (curve) {
+            case EAGEN_CURVE_PALLAS: table_entry<Pallas::Base>(base, id, out); break;
+            case EAGEN_CURVE_VESTA: table_entry<Vesta::Base>(base, id, out); break;
+            case EAGEN_CURVE_GRUMPKIN: table_entry<Grumpkin::Base>(base, id, out); break;
+            default: throw StatusError{EAGEN_E_ARG, "unknown curve id"};
+        }
+    });
 }
 
 int eagen_fft_precomp(int curve, int which, uint64_t exp, uint64_t* out) {

@@ -84,6 +84,9 @@ int eagen_profile_json(eagen_ctx* ctx, char* buf, size_t cap);
  * order / isqrt / logb_ceil: d = logb_ceil(isqrt(order)+2, base) + 1      src/argument_witness_calc.rs:32-40,54-56,89-91 */
 int eagen_num_digits(int curve, uint8_t base, uint32_t* d);
 
+/* table_entry_by_id over the curve's BASE field (host side, no device needed)      src/negbase_utils.rs:58-77 */
+int eagen_table_entry_by_id(int curve, uint8_t base, size_t id, uint64_t* out);
+
 /* ---- the hot path, host buffers in / host buffers out ------------------------------------------------- */
 
 /* negbase_decompose + pad + reverse for n scalars            src/negbase_utils.rs:20-36, argument_witness_calc.rs:93-101

@@ -124,6 +124,9 @@ namespace negbase_utils {
 inline std::optional<size_t> id_by_digit(uint8_t digit) { if (digit == 0) return std::nullopt; return (size_t)(digit - 1); }
 inline uint8_t digit_by_id(size_t id) { return (uint8_t)(id + 1); }
 
+// reference: table_entry_by_id::<F>, src/negbase_utils.rs:58-77 (F = the curve's base field)
+inline Felt table_entry_by_id(eagen_curve curve, uint8_t base, size_t id) { Felt o; eagen_table_entry_by_id(curve, base, id, o.data()); return o; }
+
 // reference: negbase_decompose + pad + reverse for n scalars (src/negbase_utils.rs:20-36, argument_witness_calc.rs:99-101):
 // n x d digits, most significant first
 inline std::vector<uint8_t> negbase_decompose(const Context& ctx, const std::vector<Felt>& scalars, uint8_t base, uint32_t* d_out = nullptr) {

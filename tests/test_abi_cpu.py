@@ -139,3 +139,12 @@ def test_cpp_host_mirror_compiles_links_and_runs(eagen, tmp_path):
                            "-L", libdir, "-leagen_msm", "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_table_entry_by_id_matches_oracle_and_known_answers(eagen, oracle):
+    p = pyref.FIELDS["pallas_fp"]
+    for idx, v in {0: 0, 1: -5, 2: 25, 3: 20, 5: -130, 11: 645}.items():
+        assert oracle.unpack_felts(eagen.table_entry_by_id(eagen.PALLAS, 5, idx), p)[0] == v % p
+    for cname, fid in (("pallas", 0), ("vesta", 1), ("grumpkin", 2)):
+        for base, idx in ((5, 1023), (17, 77), (2, 32767), (255, 9)):
+            assert (eagen.table_entry_by_id(eagen.CURVE_IDS[cname], base, idx) == oracle.table_entry_by_id(fid, base, idx)).all()
