@@ -850,7 +850,11 @@ private:
         size_t per_tree = tree_bytes(nmax);
         size_t budget = (size_t)((double)(free_b + pooled_bytes()) * 0.80);
         uint32_t group = (uint32_t)std::max<size_t>(1, std::min<size_t>(npos, budget / std::max<size_t>(per_tree, 1)));
-        if (so) group = std::min<uint32_t>(group, (npos + 6) / 7);  // streamed output: ~7 groups so that only 1/7 of the D2H is exposed
+        if (so) {  // streamed output: several groups so that only the last group's D2H is exposed
+            const char* e = getenv("EAGEN_STREAM_GROUPS");
+            uint32_t ng = e ? (uint32_t)std::max(1, atoi(e)) : 2u;  // measured best at 2^20 (tools/e2e_groups.py)
+            group = std::min<uint32_t>(group, (npos + ng - 1) / ng);
+        }
         int* tree_of_pos = (int*)tree_of_pos_.ensure((size_t)d * sizeof(int));
         std::vector<Aff> roots(npos);
         for (uint32_t g0 = pos_begin; g0 < pos_end; g0 += group) {
