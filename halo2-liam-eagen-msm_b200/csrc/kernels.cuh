@@ -425,8 +425,8 @@ __global__ void k_pair_den(const Affine<FP>* __restrict__ in, size_t in_stride, 
                            size_t out_stride, int ntrees, Fe<FP>* __restrict__ den) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= out_stride * ntrees) return;
-    int tree = (int)(g / out_stride);
-    size_t k = g % out_stride;
+    int tree = (int)((uint32_t)g / (uint32_t)out_stride);   // indices < 2^32
+    size_t k = (uint32_t)g - (uint32_t)tree * (uint32_t)out_stride;
     int c = in_cnt[tree];
     Fe<FP> dv = Fe<FP>::zero();
     if ((long long)(2 * k + 1) < c) dv = pair_den(ldg_aff(in + tree * in_stride + 2 * k), ldg_aff(in + tree * in_stride + 2 * k + 1));
@@ -439,8 +439,8 @@ __global__ void k_pair_finish(const Affine<FP>* __restrict__ in, size_t in_strid
                               Affine<FP>* __restrict__ out) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= out_stride * ntrees) return;
-    int tree = (int)(g / out_stride);
-    size_t k = g % out_stride;
+    int tree = (int)((uint32_t)g / (uint32_t)out_stride);   // indices < 2^32
+    size_t k = (uint32_t)g - (uint32_t)tree * (uint32_t)out_stride;
     int c = in_cnt[tree];
     if ((long long)(2 * k) >= c) return;
     Affine<FP> p = ldg_aff(in + tree * in_stride + 2 * k);
@@ -475,8 +475,8 @@ __global__ void k_leaf_lines(const Affine<FP>* __restrict__ T, size_t t_stride, 
                              Fe<FP>* __restrict__ A /* stride 2 */, Fe<FP>* __restrict__ B /* stride 1 */) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= out_stride * ntrees) return;
-    int tree = (int)(g / out_stride);
-    size_t k = g % out_stride;
+    int tree = (int)((uint32_t)g / (uint32_t)out_stride);   // indices < 2^32
+    size_t k = (uint32_t)g - (uint32_t)tree * (uint32_t)out_stride;
     int c = t_cnt[tree];
     if ((long long)(2 * k) >= c) return;
     Affine<FP> p = ldg_aff(T + tree * t_stride + 2 * k);
@@ -511,8 +511,8 @@ __global__ void k_merge_desc(const Affine<FP>* __restrict__ child, size_t child_
                              MergeDesc<FP>* __restrict__ desc) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= parent_stride * ntrees) return;
-    int tree = (int)(g / parent_stride);
-    size_t j = g % parent_stride;
+    int tree = (int)((uint32_t)g / (uint32_t)parent_stride);
+    size_t j = (uint32_t)g - (uint32_t)tree * (uint32_t)parent_stride;
     int c = child_cnt[tree];
     MergeDesc<FP> dsc;
     dsc.pad[0] = dsc.pad[1] = dsc.pad[2] = 0;
@@ -594,7 +594,8 @@ k_ntt_pass(NttPass<FP> a) {
         Fe<FP> v = Fe<FP>::zero();
         if (live[r]) {
             size_t tr = lin[r] >> a.t;
-            int tree = (int)(tr / a.node_max), node = (int)(tr % a.node_max);
+            const uint32_t tr32 = (uint32_t)tr;   // transform index < 2^32: 32-bit division instead of a 64-bit div/mod pair
+            int tree = (int)(tr32 / (uint32_t)a.node_max), node = (int)(tr32 - (uint32_t)tree * (uint32_t)a.node_max);
             live[r] = node < a.counts[tree];
             if (live[r]) {
                 size_t i = lin[r] & Tmask;
@@ -775,7 +776,8 @@ k_pointwise(const MergeDesc<typename CC::Base>* __restrict__ desc, size_t nmerge
     uint32_t p = (uint32_t)(g & (((size_t)1 << t) - 1));
     uint32_t mode = desc[m].mode;
     if (mode == MERGE_ABSENT) return;
-    size_t tree = m / merges_per_tree, j = m % merges_per_tree;
+    const uint32_t tree32 = (uint32_t)m / (uint32_t)merges_per_tree;   // merge index < 2^32
+    size_t tree = tree32, j = (uint32_t)m - tree32 * (uint32_t)merges_per_tree;
     size_t c1 = ((tree * nodes_per_tree + 2 * j) << t) + p, c2 = c1 + ((size_t)1 << t);
     Fe<F> a1 = ldg(EA + c1), b1 = ldg(EB + c1);
     Fe<F> ra, rb;
@@ -825,7 +827,8 @@ __global__ void k_fixup(const MergeDesc<FP>* __restrict__ desc, size_t nmerges, 
     Fe<FP>* pa = PA + m * (T + 1);
     Fe<FP> q = Fe<FP>::zero();
     if (mode != MERGE_PASS) {
-        size_t tree = m / merges_per_tree, j = m % merges_per_tree;
+        const uint32_t tree32 = (uint32_t)m / (uint32_t)merges_per_tree;
+        size_t tree = tree32, j = (uint32_t)m - tree32 * (uint32_t)merges_per_tree;
         size_t n1 = tree * nodes_per_tree + 2 * j, n2 = n1 + 1;
         const Fe<FP>* a1 = A + n1 * (h + 1); const Fe<FP>* a2 = A + n2 * (h + 1);
         const Fe<FP>* b1 = B + n1 * h; const Fe<FP>* b2 = B + n2 * h;
