@@ -748,7 +748,8 @@ private:
             double bytes = 64.0 * el * pl.size();
             if (src) bytes -= 32.0 * el - 32.0 * (double)n_present * src_len;
             if (dst) bytes -= 32.0 * el - 32.0 * (double)n_present * dst_len;
-            prof_scope_.reset(new Scope(this, inverse ? "ntt_inverse" : "ntt_forward", bytes, el * t / 2.0 + (twist ? el : 0.0)));
+            prof_scope_.reset(new Scope(this, inverse ? "ntt_inverse" : "ntt_forward", bytes,
+                                        el * t / 2.0 - (t >= 2 ? 0.75 * el : 0.5 * el) + (twist ? el : 0.0)));  // stages 0/1 have w = 1
         }
         struct Closer { std::unique_ptr<Scope>& s; ~Closer() { s.reset(); } } closer{prof_scope_};
         NttPass<FB> a;

@@ -566,6 +566,30 @@ EAGEN_D uint32_t insert_zero_bit(uint32_t v, int pos) {
     return ((v >> pos) << (pos + 1)) | lo;
 }
 
+// Shared-memory tile access with an XOR swizzle of the 16-byte chunk index.  A 32-byte element is two chunks; without the
+// swizzle every power-of-two element stride maps a quarter-warp's LDS.128/STS.128 onto 2-8 times fewer bank groups than
+// lanes (measured: 58 % of the shared wavefronts were conflict replays, and the butterfly phase was bound by them, not by the
+// multiplier).  Folding three higher 3-bit groups into the low three chunk bits makes all strides 1..512 conflict free.
+EAGEN_D uint32_t ntt_swz(uint32_t e) {
+    uint32_t c = 2u * e;
+    return c ^ (((c >> 3) ^ (c >> 6) ^ (c >> 9)) & 7u);
+}
+template <class FP>
+EAGEN_D Fe<FP> ntt_lds(const uint4* sm, uint32_t e) {
+    uint32_t c = ntt_swz(e);
+    uint4 a = sm[c], b = sm[c ^ 1u];
+    Fe<FP> r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+template <class FP>
+EAGEN_D void ntt_sts(uint4* sm, uint32_t e, const Fe<FP>& r) {
+    uint32_t c = ntt_swz(e);
+    sm[c] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    sm[c ^ 1u] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+
 #ifndef EAGEN_NTT_MINBLOCKS
 #define EAGEN_NTT_MINBLOCKS 4
 #endif
@@ -573,7 +597,6 @@ template <class FP, bool INVERSE>
 __global__ void __launch_bounds__(NTT_THREADS, EAGEN_NTT_MINBLOCKS)
 k_ntt_pass(NttPass<FP> a) {
     __shared__ uint4 sm[NTT_TILE * 2];
-    Fe<FP>* s = reinterpret_cast<Fe<FP>*>(sm);
     const int k = a.s_hi - a.s_lo + 1;
     const int lw = NTT_TILE_LOG - k;
     const size_t tile = blockIdx.x;
@@ -608,7 +631,7 @@ k_ntt_pass(NttPass<FP> a) {
                 else v = ldg(a.data + lin[r]);
             }
         }
-        s[(E << lw) | wl] = v;
+        ntt_sts(sm, (E << lw) | wl, v);
     }
     __syncthreads();
 
@@ -627,21 +650,39 @@ k_ntt_pass(NttPass<FP> a) {
         const size_t w = (tile << lw) + wl;
         const size_t L = w & (((size_t)1 << a.s_lo) - 1);
         const size_t jl = ((size_t)(E & ((1u << slo) - 1)) << a.s_lo) | L;   // index inside the 2^sgl group (same for all four)
-        const Fe<FP> W0 = ldg(a.tw + (jl << (a.tw_t - 1 - sgl)));
-        const Fe<FP> W1a = ldg(a.tw + (jl << (a.tw_t - 1 - sgh)));
-        const Fe<FP> W1b = ldg(a.tw + ((jl + ((size_t)1 << sgl)) << (a.tw_t - 1 - sgh)));
-        Fe<FP> x0 = s[i0], x1 = s[i0 + d], x2 = s[i0 + 2 * d], x3 = s[i0 + 3 * d];
-        if (INVERSE) {   // decimation in time: stage slo (distance d), then stage slo+1 (distance 2d)
-            Fe<FP> v1 = mul(x1, W0), v3 = mul(x3, W0);
-            Fe<FP> y0 = add(x0, v1), y1 = sub(x0, v1), y2 = add(x2, v3), y3 = sub(x2, v3);
-            Fe<FP> u2 = mul(y2, W1a), u3 = mul(y3, W1b);
-            s[i0] = add(y0, u2); s[i0 + 2 * d] = sub(y0, u2);
-            s[i0 + d] = add(y1, u3); s[i0 + 3 * d] = sub(y1, u3);
-        } else {         // decimation in frequency: stage slo+1 (distance 2d), then stage slo (distance d)
-            Fe<FP> y0 = add(x0, x2), y2 = mul(sub(x0, x2), W1a);
-            Fe<FP> y1 = add(x1, x3), y3 = mul(sub(x1, x3), W1b);
-            s[i0] = add(y0, y1); s[i0 + d] = mul(sub(y0, y1), W0);
-            s[i0 + 2 * d] = add(y2, y3); s[i0 + 3 * d] = mul(sub(y2, y3), W0);
+        Fe<FP> x0 = ntt_lds<FP>(sm, i0), x1 = ntt_lds<FP>(sm, i0 + d), x2 = ntt_lds<FP>(sm, i0 + 2 * d), x3 = ntt_lds<FP>(sm, i0 + 3 * d);
+        if (sgl == 0) {
+            // Global stages 1 and 0: the twiddles are 1, 1 and w_4 for every thread (jl = 0), so three of the four products
+            // vanish (uniform branch).  Over a whole tree 2/t of all butterflies of a 2^t-point transform have w = 1; this
+            // round alone carries three quarters of them.  Multiplying by the Montgomery 1 would give the same bits.
+            const Fe<FP> W1b = ldg(a.tw + ((size_t)1 << (a.tw_t - 2)));   // w_4 (or its inverse)
+            if (INVERSE) {
+                Fe<FP> y0 = add(x0, x1), y1 = sub(x0, x1), y2 = add(x2, x3), y3 = sub(x2, x3);
+                Fe<FP> u3 = mul(y3, W1b);
+                ntt_sts(sm, i0, add(y0, y2)); ntt_sts(sm, i0 + 2 * d, sub(y0, y2));
+                ntt_sts(sm, i0 + d, add(y1, u3)); ntt_sts(sm, i0 + 3 * d, sub(y1, u3));
+            } else {
+                Fe<FP> y0 = add(x0, x2), y2 = sub(x0, x2);
+                Fe<FP> y1 = add(x1, x3), y3 = mul(sub(x1, x3), W1b);
+                ntt_sts(sm, i0, add(y0, y1)); ntt_sts(sm, i0 + d, sub(y0, y1));
+                ntt_sts(sm, i0 + 2 * d, add(y2, y3)); ntt_sts(sm, i0 + 3 * d, sub(y2, y3));
+            }
+        } else {
+            const Fe<FP> W0 = ldg(a.tw + (jl << (a.tw_t - 1 - sgl)));
+            const Fe<FP> W1a = ldg(a.tw + (jl << (a.tw_t - 1 - sgh)));
+            const Fe<FP> W1b = ldg(a.tw + ((jl + ((size_t)1 << sgl)) << (a.tw_t - 1 - sgh)));
+            if (INVERSE) {   // decimation in time: stage slo (distance d), then stage slo+1 (distance 2d)
+                Fe<FP> v1 = mul(x1, W0), v3 = mul(x3, W0);
+                Fe<FP> y0 = add(x0, v1), y1 = sub(x0, v1), y2 = add(x2, v3), y3 = sub(x2, v3);
+                Fe<FP> u2 = mul(y2, W1a), u3 = mul(y3, W1b);
+                ntt_sts(sm, i0, add(y0, u2)); ntt_sts(sm, i0 + 2 * d, sub(y0, u2));
+                ntt_sts(sm, i0 + d, add(y1, u3)); ntt_sts(sm, i0 + 3 * d, sub(y1, u3));
+            } else {         // decimation in frequency: stage slo+1 (distance 2d), then stage slo (distance d)
+                Fe<FP> y0 = add(x0, x2), y2 = mul(sub(x0, x2), W1a);
+                Fe<FP> y1 = add(x1, x3), y3 = mul(sub(x1, x3), W1b);
+                ntt_sts(sm, i0, add(y0, y1)); ntt_sts(sm, i0 + d, mul(sub(y0, y1), W0));
+                ntt_sts(sm, i0 + 2 * d, add(y2, y3)); ntt_sts(sm, i0 + 3 * d, mul(sub(y2, y3), W0));
+            }
         }
         __syncthreads();
     }
@@ -657,15 +698,20 @@ k_ntt_pass(NttPass<FP> a) {
             size_t w = (tile << lw) + wl;
             size_t L = w & (((size_t)1 << a.s_lo) - 1);
             size_t j = ((size_t)(E & ((1u << sigma) - 1)) << a.s_lo) | L;
+            Fe<FP> u = ntt_lds<FP>(sm, i0), v = ntt_lds<FP>(sm, i1);
+            if (sg == 0) {   // w = 1 for every butterfly of global stage 0
+                ntt_sts(sm, i0, add(u, v));
+                ntt_sts(sm, i1, sub(u, v));
+                continue;
+            }
             Fe<FP> wj = ldg(a.tw + (j << (a.tw_t - 1 - sg)));
-            Fe<FP> u = s[i0], v = s[i1];
             if (INVERSE) {
                 v = mul(v, wj);
-                s[i0] = add(u, v);
-                s[i1] = sub(u, v);
+                ntt_sts(sm, i0, add(u, v));
+                ntt_sts(sm, i1, sub(u, v));
             } else {
-                s[i0] = add(u, v);
-                s[i1] = mul(sub(u, v), wj);
+                ntt_sts(sm, i0, add(u, v));
+                ntt_sts(sm, i1, mul(sub(u, v), wj));
             }
         }
         __syncthreads();
@@ -678,7 +724,7 @@ k_ntt_pass(NttPass<FP> a) {
         uint32_t E, wl;
         if (a.s_lo == 0) { E = q & ((1u << k) - 1); wl = q >> k; }
         else { wl = q & ((1u << lw) - 1); E = q >> lw; }
-        Fe<FP> v = s[(E << lw) | wl];
+        Fe<FP> v = ntt_lds<FP>(sm, (E << lw) | wl);
         if (a.dst) {
             size_t tr = lin[r] >> a.t, i = lin[r] & Tmask;
             if ((int)i < a.dst_len) {
