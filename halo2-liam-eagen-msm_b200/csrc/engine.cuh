@@ -473,9 +473,16 @@ public:
         return best;
     }
 
+    // largest power-of-two range below isqrt(order)+2: 127 bits on the Pasta curves, 126 on Grumpkin
+    static int synth_bits() {
+        HostU256 sq = host_isqrt(host_order<FS>());
+        int top = 255;
+        while (top > 0 && !((sq.w[top / 32] >> (top % 32)) & 1)) --top;
+        return top;  // 2^top <= isqrt(order)
+    }
     void synth_dev(uint64_t seed, size_t n, void* d_scalars, void* d_pts) override {
         use();
-        launch(k_synth_inputs<CC>, n, 128, seed, n, (Fe<FS>*)d_scalars, (F*)d_pts);
+        launch(k_synth_inputs<CC>, n, 128, seed, n, synth_bits(), (Fe<FS>*)d_scalars, (F*)d_pts);
         sync_check();
     }
     void synth_host(uint64_t seed, size_t n, uint64_t* scalars, uint64_t* pts) override {
@@ -483,7 +490,7 @@ public:
         if (!n) return;
         Fe<FS>* ds = (Fe<FS>*)in_scalars_.ensure(n * 32);
         F* dp = (F*)in_points_.ensure(n * 96);
-        launch(k_synth_inputs<CC>, n, 128, seed, n, ds, dp);
+        launch(k_synth_inputs<CC>, n, 128, seed, n, synth_bits(), ds, dp);
         EAGEN_CUDA(cudaMemcpyAsync(scalars, ds, n * 32, cudaMemcpyDeviceToHost, st_));
         EAGEN_CUDA(cudaMemcpyAsync(pts, dp, n * 96, cudaMemcpyDeviceToHost, st_));
         sync_check();

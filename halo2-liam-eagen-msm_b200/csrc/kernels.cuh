@@ -992,13 +992,14 @@ EAGEN_HD uint64_t splitmix64(uint64_t& s) {
 }
 
 template <class CC>
-__global__ void k_synth_inputs(uint64_t seed, size_t n, Fe<typename CC::Scalar>* __restrict__ scalars, Fe<typename CC::Base>* __restrict__ jac) {
+__global__ void k_synth_inputs(uint64_t seed, size_t n, int scalar_bits /* <= 127: below isqrt(order)+2 */,
+                               Fe<typename CC::Scalar>* __restrict__ scalars, Fe<typename CC::Base>* __restrict__ jac) {
     typedef typename CC::Base F;
     typedef typename CC::Scalar S;
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     uint64_t st = seed ^ (0xD1B54A32D192ED03ull * (j + 1));
-    uint64_t lo = splitmix64(st), hi = splitmix64(st) >> 1;  // 127 bits
+    uint64_t lo = splitmix64(st), hi = splitmix64(st) >> (128 - scalar_bits);  // scalar_bits in (64, 127]
     Fe<S> sc = Fe<S>::zero();
     sc.v[0] = (uint32_t)lo; sc.v[1] = (uint32_t)(lo >> 32); sc.v[2] = (uint32_t)hi; sc.v[3] = (uint32_t)(hi >> 32);
     stg(scalars + j, from_canonical(sc));

@@ -155,7 +155,7 @@ int eagen_eval_function(eagen_ctx* ctx, const uint64_t* a, size_t la, const uint
                         const uint64_t* pts, size_t n, uint64_t* out);
 
 /* ---- synthetic inputs (tests / bench.py) ------------------------------------------------
- * n scalars uniform in [0, 2^127) (Montgomery, scalar field) and n distinct points (a + j*b)*G as Jacobian triples
+ * n scalars uniform in [0, 2^k), 2^k <= isqrt(order) (k = 127 on Pasta, 126 on Grumpkin; Montgomery, scalar field) and n distinct points (a + j*b)*G as Jacobian triples
  * with non-trivial z, both functions of `seed` only.  Host-buffer and device-pointer variants.               */
 int eagen_synth_inputs(eagen_ctx* ctx, uint64_t seed, size_t n, uint64_t* scalars, uint64_t* pts);
 int eagen_dev_synth_inputs(eagen_ctx* ctx, uint64_t seed, size_t n, void* d_scalars, void* d_pts);

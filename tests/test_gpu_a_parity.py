@@ -302,3 +302,15 @@ def test_lhs_witness_streamed_output(gpu_ctx, oracle, eagen):
     with pytest.raises(eagen.EagenError) as e:
         ctx.compute_lhs_witness_stream(S.ctypes.data, P.ctypes.data, n, 5, buf.ctypes.data, total - 32)
     assert e.value.status == eagen.E_LEN
+
+
+@pytest.mark.parametrize("cname", CURVES)
+def test_synthetic_inputs_are_valid_for_every_curve(gpu_ctx, oracle, eagen, cname):
+    """the device-side generator stays below isqrt(order)+2 on every curve (126 bits on Grumpkin) and yields curve points"""
+    cv, ctx = pyref.Curve(cname), gpu_ctx(cname)
+    S, P = ctx.synth_inputs(0xEA6E0000, 400)
+    sq = pyref.isqrt(cv.q) + 2
+    assert all(s < sq for s in oracle.unpack_felts(S, cv.q))
+    assert len({bytes(r) for r in P}) == 400
+    res = ctx.compute_lhs_witness(S, P, 5, eagen.CANONICAL)
+    assert (res.carry == oracle.msm_naive(cv.id, S, P)).all()
