@@ -314,3 +314,26 @@ def test_synthetic_inputs_are_valid_for_every_curve(gpu_ctx, oracle, eagen, cnam
     assert len({bytes(r) for r in P}) == 400
     res = ctx.compute_lhs_witness(S, P, 5, eagen.CANONICAL)
     assert (res.carry == oracle.msm_naive(cv.id, S, P)).all()
+
+
+def test_empty_and_identity_inputs(gpu_ctx, oracle, eagen):
+    """n = 0 (every tmp list is [O]: all functions are the constant 1), all-zero scalars, all-identity points"""
+    cv, ctx = pyref.Curve("pallas"), gpu_ctx("pallas")
+    one = oracle.pack_felts([1], cv.p)[0]
+    r = ctx.compute_lhs_witness(np.zeros((0, 4), np.uint64), np.zeros((0, 12), np.uint64), 5, eagen.KEEP_DIGITS)
+    assert r.num_functions == 56 and not r.carry.any()
+    for k in range(56):
+        f = r.function(k)
+        assert len(f.a) == 1 and len(f.b) == 0 and (f.a[0] == one).all()
+    pts, sc = gen(cv, 6, 3)
+    P = oracle.pack_points(pts, cv.p)
+    for S, Pp in ((oracle.pack_felts([0] * 6, cv.q), P), (oracle.pack_felts(sc, cv.q), np.zeros((6, 12), np.uint64))):
+        ro = oracle.lhs_witness(cv.id, S, Pp, 5)
+        rg = ctx.compute_lhs_witness(S, Pp, 5, eagen.CANONICAL)
+        assert (rg.carries == ro.carries).all()
+        for k in range(ro.d):
+            f = rg.function(k)
+            assert same(f.a, ro.ca[k]) and same(f.b, ro.cb[k])
+    # compute_divisor_witness of the empty list is the constant 1 (reference: src/regular_functions_utils.rs:455)
+    f = ctx.compute_divisor_witness(np.zeros((0, 12), np.uint64))
+    assert len(f.a) == 1 and (f.a[0] == one).all() and len(f.b) == 0
