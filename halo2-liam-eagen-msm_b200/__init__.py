@@ -44,7 +44,7 @@ ABI_SYMBOLS = [
     "eagen_result_device_view", "eagen_synth_inputs", "eagen_dev_synth_inputs",
     "eagen_set_profiling", "eagen_profile_reset", "eagen_profile_json", "eagen_microbench",
     "eagen_dev_negbase", "eagen_dev_ntt", "eagen_lhs_witness_stream", "eagen_lhs_witness_stream_layout",
-    "eagen_table_entry_by_id",
+    "eagen_table_entry_by_id", "eagen_msm",
 ]
 SELFTEST_SYMBOLS = ["eagen_selftest_field", "eagen_selftest_curve", "eagen_selftest_negbase_params", "eagen_selftest_ntt_plan"]
 
@@ -82,6 +82,7 @@ def lib():
         L.eagen_lhs_witness_stream_layout.argtypes = [C.c_int, C.c_size_t, C.c_uint8, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
         L.eagen_lhs_witness_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8, C.c_uint32, C.c_void_p, C.c_size_t,
                                                C.POINTER(C.c_void_p)]
+        L.eagen_msm.argtypes = [C.c_void_p, U64P, U64P, C.c_size_t, U64P, C.POINTER(C.c_double)]
         L.eagen_dev_lhs_witness.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8, C.c_uint32, C.POINTER(C.c_void_p)]
         L.eagen_divisor_witness.argtypes = [C.c_void_p, U64P, C.c_size_t, C.c_uint32, U64P, C.POINTER(C.c_void_p)]
         L.eagen_result_num_digits.restype = C.c_uint32
@@ -355,6 +356,15 @@ class Context:
         h = C.c_void_p()
         self._chk(lib().eagen_divisor_witness(self._h, _p64(p), len(p), flags & ~PARTIAL, None, C.byref(h)))
         return WitnessResult(self, h, len(p)).function(0)
+
+    def best_multiexp(self, scalars, pts, with_time=False):
+        """sum s_j P_j for full-width scalars: (8,) affine point (reference tests' cross-check, halo2 best_multiexp)"""
+        s, p = _arr(scalars, 4), _arr(pts, 12)
+        if len(s) != len(p):
+            raise EagenError(E_LEN, "incompatible amount of coefficients")
+        out, ms = np.zeros(8, dtype=np.uint64), C.c_double()
+        self._chk(lib().eagen_msm(self._h, _p64(s), _p64(p), len(p), _p64(out), C.byref(ms)))
+        return (out, ms.value) if with_time else out
 
     # ---- helpers ---------------------------------------------------------------------------------------------
     def poly_mul(self, a, b):

@@ -269,6 +269,15 @@ int eagen_dev_synth_inputs(eagen_ctx* ctx, uint64_t seed, size_t n, void* d_scal
     return guarded(ctx, [&] { need(n == 0 || (d_scalars && d_pts), "eagen_dev_synth_inputs: null buffer"); ctx->eng->synth_dev(seed, n, d_scalars, d_pts); });
 }
 
+int eagen_msm(eagen_ctx* ctx, const uint64_t* scalars, const uint64_t* pts, size_t n, uint64_t* out_affine, double* device_ms) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] {
+        need(out_affine && (n == 0 || (scalars && pts)), "eagen_msm: null buffer");
+        double ms = ctx->eng->msm_host(scalars, pts, n, out_affine);
+        if (device_ms) *device_ms = ms;
+    });
+}
+
 int eagen_poly_mul(eagen_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* b, size_t lb, uint64_t* out) {
     if (!ctx) return EAGEN_E_ARG;
     return guarded(ctx, [&] { need((la == 0 || a) && (lb == 0 || b) && (la + lb <= 1 || out), "eagen_poly_mul: null buffer"); ctx->eng->poly_mul_host(a, la, b, lb, out); });

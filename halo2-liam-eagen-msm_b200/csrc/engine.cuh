@@ -142,6 +142,7 @@ struct IEngine {
     virtual void carry_chain_dev(const void* d_sums, int nparts, uint8_t base, void* d_carries) = 0;
     virtual double negbase_dev(const void* d_scalars, size_t n, uint8_t base, void* d_planes, void* d_rows) = 0;
     virtual double ntt_dev(void* d_data, uint32_t log_n, size_t batch, int inverse) = 0;
+    virtual double msm_host(const uint64_t* scalars, const uint64_t* pts, size_t n, uint64_t* out_affine) = 0;
     virtual double microbench(int which) = 0;
     virtual void set_profiling(bool on) = 0;
     virtual std::string profile_json() = 0;
@@ -447,6 +448,49 @@ public:
         float ms = 0; EAGEN_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
         res->device_ms = ms;
         return res.release();
+    }
+
+    // best_multiexp equivalent: sum s_j P_j for full-width scalars (Montgomery, scalar field) and Jacobian points; returns the
+    // device milliseconds of the compute part
+    double msm_host(const uint64_t* scalars, const uint64_t* pts, size_t n, uint64_t* out_affine) override {
+        use();
+        if (n == 0) { std::memset(out_affine, 0, 64); return 0.0; }
+        if (n >= ((size_t)1 << 32)) throw StatusError{EAGEN_E_ARG, "eagen_msm: more than 2^32 points"};
+        Fe<FS>* ds = (Fe<FS>*)in_scalars_.ensure(n * 32);
+        F* dp = (F*)in_points_.ensure(n * 96);
+        EAGEN_CUDA(cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, st_));
+        EAGEN_CUDA(cudaMemcpyAsync(dp, pts, n * 96, cudaMemcpyHostToDevice, st_));
+        EAGEN_CUDA(cudaEventRecord(ev0_, st_));
+        Aff* A = (Aff*)tpts_.ensure(n * sizeof(Aff));
+        F* zs = (F*)den_.ensure(std::max<size_t>(n, 64) * 32);
+        launch(k_jac_z<FB>, n, 256, (const F*)dp, n, zs);
+        batch_invert(zs, n);
+        launch(k_jac_to_affine<FB>, n, 256, (const F*)dp, (const F*)zs, n, A);
+        int chunks = (int)((n + MSM_CHUNK - 1) / MSM_CHUNK);
+        uint8_t* dig = (uint8_t*)planes_.ensure((size_t)MSM_WINDOWS * n);
+        uint32_t* hist = (uint32_t*)cnt_.ensure((size_t)MSM_WINDOWS * chunks * 256 * sizeof(uint32_t));
+        uint32_t* bstart = (uint32_t*)tree_n_.ensure((size_t)MSM_WINDOWS * 257 * sizeof(uint32_t));
+        uint32_t* sorted = (uint32_t*)ea_.ensure((size_t)MSM_WINDOWS * n * sizeof(uint32_t));
+        Prj* buckets = (Prj*)partials_.ensure((size_t)MSM_WINDOWS * 256 * sizeof(Prj));
+        Prj* wsum = (Prj*)sums_.ensure((size_t)(MSM_WINDOWS + 1) * sizeof(Prj));
+        {
+            Scope ps(this, "msm", (double)n * (32.0 + 96.0 + 64.0 + 32.0 * (1 + 4 + 4 + 64)), (double)n * (1.0 + 5.0 + 32.0 * 13.0));
+            launch(k_msm_digits<FS>, n, 128, (const Fe<FS>*)ds, n, dig);
+            launch2d(k_msm_hist, dim3(chunks, MSM_WINDOWS), 256, (const uint8_t*)dig, n, chunks, hist);
+            launch2d(k_msm_scan, dim3(MSM_WINDOWS, 1), 256, hist, chunks, bstart);
+            launch2d(k_msm_scatter, dim3(chunks, MSM_WINDOWS), 256, (const uint8_t*)dig, n, chunks, (const uint32_t*)hist, sorted);
+            launch(k_msm_buckets<CC>, (size_t)MSM_WINDOWS * 255 * 32, 128, (const Aff*)A, n, (const uint32_t*)sorted, (const uint32_t*)bstart, buckets);
+            launch(k_msm_window_sums<CC>, MSM_WINDOWS, 32, (const Prj*)buckets, wsum);
+            launch(k_msm_combine<CC>, 1, 32, (const Prj*)wsum, wsum + MSM_WINDOWS, zs);
+        }
+        batch_invert(zs, 1);
+        Aff* res = (Aff*)carries_.ensure(sizeof(Aff) * 64);
+        launch(k_proj_to_affine<FB>, 1, 32, (const Prj*)(wsum + MSM_WINDOWS), (const F*)zs, (size_t)1, res);
+        EAGEN_CUDA(cudaEventRecord(ev1_, st_));
+        EAGEN_CUDA(cudaMemcpyAsync(out_affine, res, 64, cudaMemcpyDeviceToHost, st_));
+        sync_check();
+        float ms = 0; EAGEN_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+        return ms;
     }
 
     // which = 0: 32-bit IMAD per second; which = 1: base-field Montgomery products per second (register-resident chains)

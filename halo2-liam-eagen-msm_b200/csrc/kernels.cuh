@@ -1023,6 +1023,125 @@ __global__ void k_synth_inputs(uint64_t seed, size_t n, int scalar_bits /* <= 12
 }
 
 // ------------------------------------------------------------------------------------------------
+// Windowed bucket MSM over full-width scalars (the `best_multiexp` the reference's tests compare the carry with:
+// src/argument_witness_calc.rs:144, src/regular_functions_utils.rs:655).  c = 8 bit windows = the bytes of the canonical
+// scalar; per window a counting sort of the point indices by digit, one warp per bucket (complete mixed additions, shared
+// memory tree reduce), a running-sum pass per window and a Horner combine.  SURVEY.md section 8f rank 1.
+// ------------------------------------------------------------------------------------------------
+constexpr int MSM_WINDOWS = 32;
+constexpr int MSM_CHUNK = 1024;
+
+template <class FS>
+__global__ void k_msm_digits(const Fe<FS>* __restrict__ scalars, size_t n, uint8_t* __restrict__ digits /* 32 x n */) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    Fe<FS> x = to_canonical(ldg(scalars + j));
+#pragma unroll
+    for (int w = 0; w < MSM_WINDOWS; ++w) digits[(size_t)w * n + j] = (uint8_t)(x.v[w >> 2] >> (8 * (w & 3)));
+}
+
+static __global__ void k_msm_hist(const uint8_t* __restrict__ digits, size_t n, int chunks, uint32_t* __restrict__ hist /* 32 x chunks x 256 */) {
+    __shared__ uint32_t cnt[256];
+    const int w = blockIdx.y;
+    cnt[threadIdx.x] = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < MSM_CHUNK; k += blockDim.x) {
+        size_t j = (size_t)blockIdx.x * MSM_CHUNK + k;
+        if (j < n) atomicAdd(&cnt[digits[(size_t)w * n + j]], 1u);
+    }
+    __syncthreads();
+    hist[((size_t)w * chunks + blockIdx.x) * 256 + threadIdx.x] = cnt[threadIdx.x];
+}
+
+// one block of 256 threads per window: bucket starts, then per-(chunk, bucket) write offsets in place of the counts
+static __global__ void k_msm_scan(uint32_t* __restrict__ hist, int chunks, uint32_t* __restrict__ bstart /* 32 x 257 */) {
+    __shared__ uint32_t tot[256];
+    const int w = blockIdx.x, b = threadIdx.x;
+    uint32_t* h = hist + (size_t)w * chunks * 256;
+    uint32_t t = 0;
+    for (int c = 0; c < chunks; ++c) t += h[(size_t)c * 256 + b];
+    tot[b] = t;
+    __syncthreads();
+    if (b == 0) {
+        uint32_t off = 0;
+        for (int i = 0; i < 256; ++i) { uint32_t v = tot[i]; tot[i] = off; bstart[w * 257 + i] = off; off += v; }
+        bstart[w * 257 + 256] = off;
+    }
+    __syncthreads();
+    uint32_t off = tot[b];
+    for (int c = 0; c < chunks; ++c) { uint32_t v = h[(size_t)c * 256 + b]; h[(size_t)c * 256 + b] = off; off += v; }
+}
+
+static __global__ void k_msm_scatter(const uint8_t* __restrict__ digits, size_t n, int chunks, const uint32_t* __restrict__ hist,
+                                     uint32_t* __restrict__ sorted /* 32 x n */) {
+    __shared__ uint32_t cur[256];
+    const int w = blockIdx.y;
+    cur[threadIdx.x] = hist[((size_t)w * chunks + blockIdx.x) * 256 + threadIdx.x];
+    __syncthreads();
+    for (int k = threadIdx.x; k < MSM_CHUNK; k += blockDim.x) {
+        size_t j = (size_t)blockIdx.x * MSM_CHUNK + k;
+        if (j < n) {
+            uint32_t pos = atomicAdd(&cur[digits[(size_t)w * n + j]], 1u);   // order inside a bucket is irrelevant for a sum
+            sorted[(size_t)w * n + pos] = (uint32_t)j;
+        }
+    }
+}
+
+// one warp per (window, bucket >= 1)
+template <class CC>
+__global__ void __launch_bounds__(128)
+k_msm_buckets(const Affine<typename CC::Base>* __restrict__ pts, size_t n, const uint32_t* __restrict__ sorted,
+              const uint32_t* __restrict__ bstart, Proj<typename CC::Base>* __restrict__ buckets /* 32 x 256 */) {
+    typedef typename CC::Base F;
+    __shared__ Proj<F> sm[128];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gw = blockIdx.x * 4 + wid;          // global warp = w * 255 + (bucket - 1)
+    const int w = gw / 255, b = gw % 255 + 1;
+    Proj<F> acc = Proj<F>::identity();
+    if (w < MSM_WINDOWS) {
+        const uint32_t lo = bstart[w * 257 + b], hi = bstart[w * 257 + b + 1];
+        for (uint32_t i = lo + lane; i < hi; i += 32) {
+            Affine<F> q = ldg_aff(pts + sorted[(size_t)w * n + i]);
+            if (!q.is_identity()) acc = padd_mixed<CC>(acc, q);
+        }
+    }
+    sm[threadIdx.x] = acc;
+    __syncwarp();
+    for (int s = 16; s > 0; s >>= 1) {
+        if (lane < s) sm[threadIdx.x] = padd<CC>(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncwarp();
+    }
+    if (lane == 0 && w < MSM_WINDOWS) buckets[w * 256 + b] = sm[threadIdx.x];
+}
+
+// S_w = sum_b b * B_b by running sums; one thread per window
+template <class CC>
+__global__ void k_msm_window_sums(const Proj<typename CC::Base>* __restrict__ buckets, Proj<typename CC::Base>* __restrict__ wsum) {
+    typedef typename CC::Base F;
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= MSM_WINDOWS) return;
+    Proj<F> run = Proj<F>::identity(), sum = Proj<F>::identity();
+    for (int b = 255; b >= 1; --b) {
+        run = padd<CC>(run, buckets[w * 256 + b]);
+        sum = padd<CC>(sum, run);
+    }
+    wsum[w] = sum;
+}
+
+template <class CC>
+__global__ void k_msm_combine(const Proj<typename CC::Base>* __restrict__ wsum, Proj<typename CC::Base>* __restrict__ out, Fe<typename CC::Base>* __restrict__ z) {
+    typedef typename CC::Base F;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Proj<F> r = Proj<F>::identity();
+    for (int w = MSM_WINDOWS - 1; w >= 0; --w) {
+        for (int k = 0; k < 8; ++k) r = pdbl<CC>(r);
+        r = padd<CC>(r, wsum[w]);
+    }
+    out[0] = r;
+    stg(z, r.z);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Integer-pipe micro-benchmarks: the roofline denominators MEASURED_PEAKS.json does not carry.
 //   k_imad_peak   : 16 independent 32-bit IMAD chains per thread, no memory traffic  -> IMAD/s of the chip
 //   k_modmul_peak : 4 independent Montgomery-product chains per thread               -> modmul/s ceiling of mul()

@@ -132,6 +132,11 @@ size_t eagen_result_total_bytes(const eagen_result* r);
 double eagen_result_device_ms(const eagen_result* r);
 void eagen_result_free(eagen_result* r);
 
+/* best_multiexp(coeffs, bases): sum s_j P_j for FULL-WIDTH scalars (windowed bucket method on the device).  The reference only
+ * uses it in its tests, as the cross-check of the witness carry        src/argument_witness_calc.rs:144, regular_functions_utils.rs:655
+ * scalars: n x 32 B Montgomery (scalar field); pts: n Jacobian points; out: affine (64 B).  device_ms may be NULL. */
+int eagen_msm(eagen_ctx* ctx, const uint64_t* scalars, const uint64_t* pts, size_t n, uint64_t* out_affine, double* device_ms);
+
 /* ---- helper API of regular_functions_utils ------------------------------------------------------------ */
 
 /* &Polynomial * &Polynomial                                   src/regular_functions_utils.rs:209-216

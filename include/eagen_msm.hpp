@@ -157,6 +157,14 @@ inline std::vector<AffinePoint> precompute_multiplicities(const Context& ctx, co
     return out;
 }
 
+// halo2 best_multiexp(coeffs, bases) as the reference's tests use it (src/argument_witness_calc.rs:144)
+inline AffinePoint best_multiexp(const Context& ctx, const std::vector<Felt>& scalars, const std::vector<JacobianPoint>& pts) {
+    if (scalars.size() != pts.size()) throw Error(EAGEN_E_LEN, "incompatible amount of coefficients");
+    AffinePoint out{};
+    ctx.check(eagen_msm(ctx.raw(), scalars.empty() ? nullptr : scalars[0].data(), pts.empty() ? nullptr : pts[0].data(), pts.size(), out.data(), nullptr));
+    return out;
+}
+
 struct LhsWitness {
     AffinePoint carry;                                              // sum s_j P_j
     std::vector<regular_functions_utils::RegularFunction> functions;  // index k <-> coefficient of (-base)^k

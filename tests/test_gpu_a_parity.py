@@ -337,3 +337,22 @@ def test_empty_and_identity_inputs(gpu_ctx, oracle, eagen):
     # compute_divisor_witness of the empty list is the constant 1 (reference: src/regular_functions_utils.rs:455)
     f = ctx.compute_divisor_witness(np.zeros((0, 12), np.uint64))
     assert len(f.a) == 1 and (f.a[0] == one).all() and len(f.b) == 0
+
+
+@pytest.mark.parametrize("cname", CURVES)
+def test_best_multiexp_full_width_scalars(gpu_ctx, oracle, eagen, cname):
+    """the windowed bucket MSM (reference tests' cross-check `best_multiexp`) against double-and-add on the oracle side"""
+    cv, ctx = pyref.Curve(cname), gpu_ctx(cname)
+    rng = pyref.SplitMix64(77)
+    for n in (1, 2, 100, 3000):
+        pts, _ = gen(cv, n, 500 + n)
+        sc = [rng.next_bits(4) % cv.q for _ in range(n)]
+        if n >= 100:
+            sc[3], sc[4], pts[5] = 0, cv.q - 1, None
+        zs = [rng.next_bits(4) % cv.p or 1 for _ in range(n)]
+        S, P = oracle.pack_felts(sc, cv.q), oracle.pack_points(pts, cv.p, zs)
+        assert (ctx.best_multiexp(S, P) == oracle.msm_naive(cv.id, S, P)).all(), n
+    assert not ctx.best_multiexp(np.zeros((0, 4), np.uint64), np.zeros((0, 12), np.uint64)).any()
+    # and the identity the reference's lhs_test asserts: witness carry == best_multiexp (src/argument_witness_calc.rs:144-147)
+    S, P = ctx.synth_inputs(31337, 2000)
+    assert (ctx.compute_lhs_witness(S, P, 5, eagen.NO_FUNCTIONS).carry == ctx.best_multiexp(S, P)).all()
