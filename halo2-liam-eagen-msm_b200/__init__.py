@@ -32,6 +32,10 @@ E_ARG, E_LEN, E_RANGE, E_SUM_NONZERO, E_NTT_TOO_LARGE, E_CUDA, E_NCCL, E_DIGITS,
 U64P = C.POINTER(C.c_uint64)
 U8P = C.POINTER(C.c_uint8)
 
+PSW_FAITHFUL, PSW_INTENDED = 0, 1
+# one Entry of prepare_scalar_witness (32 bytes)
+PSW_DTYPE = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("mask", "<u4"), ("kind", "<u4"), ("zero", "<u8")])
+
 # every symbol include/eagen_msm.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
     "eagen_ctx_create", "eagen_ctx_destroy", "eagen_last_error", "eagen_status_string", "eagen_launch_count",
@@ -44,9 +48,10 @@ ABI_SYMBOLS = [
     "eagen_result_device_view", "eagen_synth_inputs", "eagen_dev_synth_inputs",
     "eagen_set_profiling", "eagen_profile_reset", "eagen_profile_json", "eagen_microbench",
     "eagen_dev_negbase", "eagen_dev_ntt", "eagen_lhs_witness_stream", "eagen_lhs_witness_stream_layout",
-    "eagen_table_entry_by_id", "eagen_msm",
+    "eagen_table_entry_by_id", "eagen_msm", "eagen_prepare_scalar_witness", "eagen_divisor_witness_naive",
 ]
-SELFTEST_SYMBOLS = ["eagen_selftest_field", "eagen_selftest_curve", "eagen_selftest_negbase_params", "eagen_selftest_ntt_plan"]
+SELFTEST_SYMBOLS = ["eagen_selftest_field", "eagen_selftest_curve", "eagen_selftest_negbase_params", "eagen_selftest_negbase_digits",
+                    "eagen_selftest_ntt_plan"]
 
 
 class EagenError(RuntimeError):
@@ -119,9 +124,12 @@ def lib():
         L.eagen_profile_json.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
         L.eagen_synth_inputs.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t, U64P, U64P]
         L.eagen_dev_synth_inputs.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.eagen_prepare_scalar_witness.argtypes = [C.c_void_p, U64P, C.c_size_t, C.c_uint8, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t]
+        L.eagen_divisor_witness_naive.argtypes = [C.c_void_p, U64P, C.c_size_t, U64P, C.POINTER(C.c_size_t), U64P, C.POINTER(C.c_size_t)]
         L.eagen_selftest_field.argtypes = [C.c_int, C.c_int, U64P, U64P, U64P]
         L.eagen_selftest_curve.argtypes = [C.c_int, C.c_int, U64P, U64P, C.c_uint32, U64P]
         L.eagen_selftest_negbase_params.argtypes = [C.c_int, C.c_uint8, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.eagen_selftest_negbase_digits.argtypes = [C.c_int, C.c_uint8, U64P, U8P, C.POINTER(C.c_int)]
         L.eagen_selftest_ntt_plan.argtypes = [C.c_int, C.POINTER(C.c_int)]
         _lib = L
     return _lib
@@ -393,6 +401,25 @@ class Context:
         self._chk(lib().eagen_eval_function(self._h, _p64(a), len(a), _p64(b), len(b), _p64(p), len(p), _p64(out)))
         return out
 
+    def prepare_scalar_witness(self, scalars, base, num_digits, logtable, mode=PSW_FAITHFUL):
+        """reference: src/negbase_utils.rs:79-124 for every scalar.  Returns a structured array [n][base][num_limbs+1] with fields
+        lo, hi (two's complement i128 halves), mask, kind (0 Scalar, 1 Bucket, 2 Limb)"""
+        s = _arr(scalars, 4)
+        num_limbs = (num_digits + logtable - 1) // logtable
+        out = np.zeros((len(s), base, num_limbs + 1), dtype=PSW_DTYPE)
+        self._chk(lib().eagen_prepare_scalar_witness(self._h, _p64(s), len(s), C.c_uint8(base), num_digits, logtable, mode,
+                                                     out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def compute_divisor_witness_naive(self, pts):
+        """reference: src/regular_functions_utils.rs:483-551.  Returns (pos, neg): arrays (k, 3, 4) of lines lx | ly | lz"""
+        p = _arr(pts, 12)
+        n = len(p)
+        pos, neg = np.zeros((max(n, 1), 3, 4), dtype=np.uint64), np.zeros((max(n, 1), 3, 4), dtype=np.uint64)
+        npos, nneg = C.c_size_t(len(pos)), C.c_size_t(len(neg))
+        self._chk(lib().eagen_divisor_witness_naive(self._h, _p64(p), n, _p64(pos), C.byref(npos), _p64(neg), C.byref(nneg)))
+        return pos[: npos.value], neg[: nneg.value]
+
     def synth_inputs(self, seed, n):
         """deterministic synthetic (scalars (n,4), Jacobian points (n,12)) generated on the device"""
         sc, pt = np.zeros((n, 4), dtype=np.uint64), np.zeros((n, 12), dtype=np.uint64)
@@ -447,13 +474,26 @@ def selftest_curve(curve, op, p, q=None, k=0):
 
 
 def selftest_negbase_params(curve, base):
-    d, chunk, cd = C.c_uint32(), C.c_uint32(), C.c_uint32()
-    limbs = (C.c_uint32 * 24)()
-    rc = lib().eagen_selftest_negbase_params(curve, C.c_uint8(base), C.byref(d), C.byref(chunk), C.byref(cd), limbs)
+    d, group, words = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    limbs = (C.c_uint32 * 32)()
+    rc = lib().eagen_selftest_negbase_params(curve, C.c_uint8(base), C.byref(d), C.byref(group), C.byref(words), limbs)
     if rc:
         raise EagenError(rc, "selftest_negbase_params")
     to_int = lambda ws: sum(int(w) << (32 * i) for i, w in enumerate(ws))
-    return dict(d=d.value, chunk=chunk.value, chunk_digits=cd.value, sq=to_int(limbs[0:8]), K=to_int(limbs[8:16]), bd=to_int(limbs[16:24]))
+    return dict(d=d.value, group=group.value, words=words.value, sq=to_int(limbs[0:8]), K=to_int(limbs[8:16]), bd=to_int(limbs[16:24]),
+                inv=to_int(limbs[24:32]))
+
+
+def selftest_negbase_digits(curve, base, scalar):
+    """K1's per-scalar arithmetic on the host (same source as the kernel): (digits MSD first, kernel error flag)"""
+    s = _arr(scalar)
+    d = num_digits(curve, base)
+    out = np.zeros(d, dtype=np.uint8)
+    kerr = C.c_int()
+    rc = lib().eagen_selftest_negbase_digits(curve, C.c_uint8(base), _p64(s), out.ctypes.data_as(U8P), C.byref(kerr))
+    if rc:
+        raise EagenError(rc, "selftest_negbase_digits")
+    return out, kerr.value
 
 
 def selftest_ntt_plan(t):

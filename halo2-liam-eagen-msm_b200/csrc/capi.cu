@@ -278,6 +278,24 @@ int eagen_msm(eagen_ctx* ctx, const uint64_t* scalars, const uint64_t* pts, size
     });
 }
 
+int eagen_prepare_scalar_witness(eagen_ctx* ctx, const uint64_t* scalars, size_t n, uint8_t base, uint32_t num_digits, uint32_t logtable,
+                                 int mode, void* out, size_t out_bytes) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] {
+        need(base >= 2 && logtable >= 1 && (n == 0 || (scalars && out)), "eagen_prepare_scalar_witness: bad arguments");
+        size_t num_limbs = ((size_t)num_digits + logtable - 1) / logtable;
+        if (out_bytes < n * (size_t)base * (num_limbs + 1) * 32) throw StatusError{EAGEN_E_LEN, "eagen_prepare_scalar_witness: output buffer too small"};
+        ctx->eng->scalar_witness_host(scalars, n, base, num_digits, logtable, mode, out);
+    });
+}
+int eagen_divisor_witness_naive(eagen_ctx* ctx, const uint64_t* pts, size_t n, uint64_t* pos_lines, size_t* n_pos, uint64_t* neg_lines, size_t* n_neg) {
+    if (!ctx || !n_pos || !n_neg) return EAGEN_E_ARG;
+    return guarded(ctx, [&] {
+        need(n == 0 || (pts && pos_lines && neg_lines), "eagen_divisor_witness_naive: null buffer");
+        ctx->eng->naive_host(pts, n, pos_lines, n_pos, neg_lines, n_neg);
+    });
+}
+
 int eagen_poly_mul(eagen_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* b, size_t lb, uint64_t* out) {
     if (!ctx) return EAGEN_E_ARG;
     return guarded(ctx, [&] { need((la == 0 || a) && (lb == 0 || b) && (la + lb <= 1 || out), "eagen_poly_mul: null buffer"); ctx->eng->poly_mul_host(a, la, b, lb, out); });
@@ -406,10 +424,24 @@ template <class CC> void st_curve(int op, const uint64_t* p, const uint64_t* q, 
     Affine<F> o = proj_to_affine(r, inv(r.z));
     std::memcpy(out, &o, 64);
 }
-template <class FS> void st_nb(uint8_t base, uint32_t* d, uint32_t* chunk, uint32_t* cd, uint32_t* limbs) {
+template <class FS> void st_nb(uint8_t base, uint32_t* d, uint32_t* group, uint32_t* words, uint32_t* limbs) {
     NegbaseParams p = make_negbase_params<FS>(base);
-    *d = p.d; *chunk = p.chunk; *cd = p.chunk_digits;
+    *d = p.d; *group = p.g; *words = p.nw;
     std::memcpy(limbs, p.sq, 32); std::memcpy(limbs + 8, p.K, 32); std::memcpy(limbs + 16, p.bd, 32);
+    std::memset(limbs + 24, 0, 32); std::memcpy(limbs + 24, p.inv, 24);
+}
+// K1's per-scalar arithmetic (from_mont + negbase_words + the table) run on the host from the kernel's own source
+template <class FS> int st_nb_digits(uint8_t base, const uint64_t* scalar, uint8_t* digits) {
+    NegbaseParams p = make_negbase_params<FS>(base);
+    std::vector<uint32_t> lut(p.lut_n);
+    for (uint32_t v = 0; v < p.lut_n; ++v) lut[v] = negbase_lut_entry(v, p.base, p.g);
+    Fe<FS> xm; std::memcpy(xm.v, scalar, 32);
+    uint32_t x[8], words[NEGBASE_MAX_WORDS];
+    from_mont<FS>(xm.v, x);
+    int e = negbase_words(x, p, lut.data(), words, 1);
+    for (uint32_t w = 0; w < p.nw; ++w)
+        for (int k = 0; k < 4; ++k) { int pos = (int)(4 * w + k) - (int)p.pad; if (pos >= 0) digits[pos] = (uint8_t)(words[w] >> (8 * k)); }
+    return e;
 }
 }  // namespace
 
@@ -444,6 +476,17 @@ int eagen_selftest_negbase_params(int curve, uint8_t base, uint32_t* d, uint32_t
             case EAGEN_CURVE_PALLAS: st_nb<Pallas::Scalar>(base, d, chunk, cd, limbs); break;
             case EAGEN_CURVE_VESTA: st_nb<Vesta::Scalar>(base, d, chunk, cd, limbs); break;
             case EAGEN_CURVE_GRUMPKIN: st_nb<Grumpkin::Scalar>(base, d, chunk, cd, limbs); break;
+            default: throw StatusError{EAGEN_E_ARG, "unknown curve id"};
+        }
+    });
+}
+int eagen_selftest_negbase_digits(int curve, uint8_t base, const uint64_t* scalar, uint8_t* digits, int* kerr) {
+    return guarded(nullptr, [&] {
+        need(scalar && digits && kerr && base >= 2, "bad arguments");
+        switch (curve) {
+            case EAGEN_CURVE_PALLAS: *kerr = st_nb_digits<Pallas::Scalar>(base, scalar, digits); break;
+            case EAGEN_CURVE_VESTA: *kerr = st_nb_digits<Vesta::Scalar>(base, scalar, digits); break;
+            case EAGEN_CURVE_GRUMPKIN: *kerr = st_nb_digits<Grumpkin::Scalar>(base, scalar, digits); break;
             default: throw StatusError{EAGEN_E_ARG, "unknown curve id"};
         }
     });

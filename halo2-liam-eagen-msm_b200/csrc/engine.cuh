@@ -143,6 +143,8 @@ struct IEngine {
     virtual double negbase_dev(const void* d_scalars, size_t n, uint8_t base, void* d_planes, void* d_rows) = 0;
     virtual double ntt_dev(void* d_data, uint32_t log_n, size_t batch, int inverse) = 0;
     virtual double msm_host(const uint64_t* scalars, const uint64_t* pts, size_t n, uint64_t* out_affine) = 0;
+    virtual void scalar_witness_host(const uint64_t* scalars, size_t n, uint8_t base, uint32_t num_digits, uint32_t logtable, int mode, void* out) = 0;
+    virtual void naive_host(const uint64_t* pts, size_t n, uint64_t* pos, size_t* n_pos, uint64_t* neg, size_t* n_neg) = 0;
     virtual double microbench(int which) = 0;
     virtual void set_profiling(bool on) = 0;
     virtual std::string profile_json() = 0;
@@ -217,27 +219,30 @@ inline NegbaseParams make_negbase_params(uint8_t base) {
     }
     std::memcpy(p.K, K.w, 32);
     std::memcpy(p.bd, pw.w, 32);
-    p.chunk_digits = 0; p.chunk = 1;
-    while ((uint64_t)p.chunk * base <= (1u << 15)) { p.chunk *= base; ++p.chunk_digits; }
-    // multiply-shift reciprocals, exact for 31-bit dividends: M = ceil(2^k / dv), k = 31 + ceil(log2 dv)
-    auto magic = [](uint32_t dv, uint32_t& m, uint32_t& k) {
-        uint32_t s = 0;
-        while ((1u << s) < dv) ++s;
-        k = 31 + s;
-        m = (uint32_t)((((uint64_t)1 << k) + dv - 1) / dv);
-    };
-    magic(p.chunk, p.chunk_magic, p.chunk_shift);
-    magic(base, p.base_magic, p.base_shift);
-    // before step s the running quotient is < base^(d - s*chunk_digits): highest possibly non-zero 16-bit half-limb
-    std::memset(p.tops, 0, sizeof p.tops);
-    for (uint32_t s = 0; s * p.chunk_digits < p.d && s < 32; ++s) {
-        HostU256 bound = HostU256::zero();
-        bound.w[0] = 1;
-        for (uint32_t i = 0; i < p.d - s * p.chunk_digits; ++i) bound.mul_small_add(base, 0);
-        int top = 15;
-        while (top > 0 && ((bound.w[top / 2] >> (16 * (top & 1))) & 0xffffu) == 0) --top;
-        p.tops[s] = (uint8_t)top;
+    // b^0 .. b^4 and the table group size
+    uint64_t pwv = 1;
+    for (int k = 0; k < 5; ++k) { p.pw[k] = (uint32_t)pwv; pwv *= base; }
+    p.g = base <= 5 ? 4 : (base <= 31 ? 2 : 1);
+    p.lut_n = p.g == 1 ? 0 : p.pw[p.g];
+    p.nw = (p.d + 3) / 4;
+    p.pad = 4 * p.nw - p.d;
+    if (p.nw > (uint32_t)NEGBASE_MAX_WORDS) throw StatusError{EAGEN_E_ARG, "negbase: more than 144 digits"};
+    // The 160-bit fixed-point image of y / b^d is exact for every digit iff 2^-160 + b^d 2^-288 <= b^-d; b^d < 2^143 suffices.
+    for (int l = 5; l < 8; ++l) if (pw.w[l]) throw StatusError{EAGEN_E_ARG, "negbase: b^d does not fit 143 bits"};
+    if (pw.w[4] >> 15) throw StatusError{EAGEN_E_ARG, "negbase: b^d does not fit 143 bits"};
+    // inv = ceil(2^288 / b^d): d nested floor divisions by b (floor(floor(x/a)/b) = floor(x/(ab))), +1 unless all were exact
+    uint32_t q[10] = {0};
+    q[9] = 1;  // 2^288
+    bool exact = true;
+    for (uint32_t i = 0; i < p.d; ++i) {
+        uint64_t rem = 0;
+        for (int l = 9; l >= 0; --l) { uint64_t cur = (rem << 32) | q[l]; q[l] = (uint32_t)(cur / base); rem = cur % base; }
+        if (rem) exact = false;
     }
+    if (!exact) { for (int l = 0; l < 10; ++l) { if (++q[l] != 0) break; } }
+    for (int l = 6; l < 10; ++l) if (q[l]) throw StatusError{EAGEN_E_ARG, "negbase: reciprocal does not fit 192 bits"};
+    if (q[5] > 1 || (q[5] == 1 && (q[0] | q[1] | q[2] | q[3] | q[4]))) throw StatusError{EAGEN_E_ARG, "negbase: b^d < 2^128"};
+    std::memcpy(p.inv, q, 24);
     return p;
 }
 
@@ -652,6 +657,97 @@ public:
         sync_check();
     }
 
+    // prepare_scalar_witness for n scalars (reference: src/negbase_utils.rs:79-124); out: n x base x (num_limbs+1) entries of 32 B
+    void scalar_witness_host(const uint64_t* scalars, size_t n, uint8_t base, uint32_t num_digits, uint32_t logtable, int mode, void* out) override {
+        use();
+        if (logtable < 1 || logtable > 24) throw StatusError{EAGEN_E_ARG, "prepare_scalar_witness: logtable must be in [1, 24]"};
+        if (num_digits < 1 || num_digits > 4096) throw StatusError{EAGEN_E_ARG, "prepare_scalar_witness: num_digits must be in [1, 4096]"};
+        if (mode != 0 && mode != 1) throw StatusError{EAGEN_E_ARG, "prepare_scalar_witness: mode must be 0 (faithful) or 1 (intended)"};
+        if (n == 0) return;
+        NegbaseParams prm = make_negbase_params<FS>(base);
+        const uint32_t num_limbs = (num_digits + logtable - 1) / logtable;
+        const size_t bytes = n * (size_t)base * (num_limbs + 1) * sizeof(PswEntry);
+        Fe<FS>* ds = (Fe<FS>*)in_scalars_.ensure(n * 32);
+        uint8_t* planes = (uint8_t*)planes_.ensure(n * prm.d);
+        PswEntry* dout = (PswEntry*)table_.ensure(bytes);
+        EAGEN_CUDA(cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, st_));
+        run_negbase(ds, n, prm, planes, nullptr);
+        {
+            Scope ps(this, "scalar_witness", (double)n * (32.0 + (double)base * prm.d) + (double)bytes, 0.0);
+            launch2d(k_scalar_witness<FS>, dim3((unsigned)((n + 127) / 128), base), 128, (const uint8_t*)planes, n, prm.d, (uint32_t)base, num_digits,
+                     logtable, num_limbs, mode, (const Fe<FS>*)ds, dout, d_err_);
+        }
+        EAGEN_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, st_));
+        sync_check();
+    }
+
+    // compute_divisor_witness_naive (reference: src/regular_functions_utils.rs:483-551).  The pairing of a round depends on which
+    // points of the list are the identity (`if inc1 != C::identity()`, :517,:533), so every round reads the identity flags back
+    // (one byte per point) and the host replays the reference's pop order into index pairs; sums, lines and the batched
+    // inversion of the slopes' denominators run on the device.  *n_pos / *n_neg: capacity in (lines), count out.
+    void naive_host(const uint64_t* pts, size_t n, uint64_t* pos, size_t* n_pos, uint64_t* neg, size_t* n_neg) override {
+        use();
+        const size_t cap_pos = *n_pos, cap_neg = *n_neg;
+        *n_pos = 0; *n_neg = 0;
+        if (n == 0) return;
+        typedef LineTriple<FB> Line;
+        F* dp = (F*)in_points_.ensure(n * 96);
+        EAGEN_CUDA(cudaMemcpyAsync(dp, pts, n * 96, cudaMemcpyHostToDevice, st_));
+        Aff* lists = (Aff*)tpts_.ensure(2 * (n + 2) * sizeof(Aff));
+        Aff* L[2] = {lists, lists + (n + 2)};          // pos, neg
+        size_t len[2] = {n, 0};
+        F* zs = (F*)den_.ensure(n * 32);
+        launch(k_jac_z<FB>, n, 256, (const F*)dp, n, zs);
+        batch_invert(zs, n);
+        launch(k_jac_to_affine<FB>, n, 256, (const F*)dp, (const F*)zs, n, L[0]);
+        Line* lines[2] = {(Line*)oa_.ensure((n + 1) * sizeof(Line)), (Line*)ob_.ensure((n + 1) * sizeof(Line))};
+        size_t nl[2] = {0, 0};
+        uint8_t* dflags = (uint8_t*)rows_.ensure(n + 2);
+        int2* dpairs = (int2*)cnt_.ensure((n / 2 + 1) * sizeof(int2));
+        std::vector<uint8_t> flags;
+        std::vector<int2> pairs;
+        auto round = [&](int from) {
+            const int to = 1 - from;
+            const size_t m = len[from];
+            if (m <= 1) return;
+            flags.resize(m);
+            launch(k_identity_flags<FB>, m, 256, (const Aff*)L[from], m, dflags);
+            EAGEN_CUDA(cudaMemcpyAsync(flags.data(), dflags, m, cudaMemcpyDeviceToHost, st_));
+            EAGEN_CUDA(cudaStreamSynchronize(st_));
+            pairs.clear();
+            size_t top = m;
+            while (top > 1) {   // :515-520
+                const size_t i1 = --top;
+                if (!flags[i1]) { const size_t i2 = --top; pairs.push_back(make_int2((int)i1, (int)i2)); }
+            }
+            len[from] = top;
+            const size_t np = pairs.size();
+            if (np == 0) return;
+            if (nl[from] + np > n + 1) throw StatusError{EAGEN_E_ARG, "compute_divisor_witness_naive: internal line buffer overflow"};
+            EAGEN_CUDA(cudaMemcpyAsync(dpairs, pairs.data(), np * sizeof(int2), cudaMemcpyHostToDevice, st_));
+            launch(k_naive_den<FB>, np, 256, (const Aff*)L[from], (const int2*)dpairs, np, zs);
+            batch_invert(zs, np);
+            launch(k_naive_finish<FB>, np, 128, (const Aff*)L[from], (const int2*)dpairs, np, (const F*)zs, L[to] + len[to], lines[from] + nl[from]);
+            EAGEN_CUDA(cudaStreamSynchronize(st_));   // `pairs` is reused by the next round
+            len[to] += np;
+            nl[from] += np;
+        };
+        while (len[0] > 1 || len[1] > 1) { round(0); round(1); }   // :513
+        Aff left[2];
+        std::memset(left, 0, sizeof left);
+        for (int s = 0; s < 2; ++s) if (len[s]) EAGEN_CUDA(cudaMemcpyAsync(&left[s], L[s], sizeof(Aff), cudaMemcpyDeviceToHost, st_));
+        sync_check();
+        const bool ok = (len[0] == 0 && len[1] == 0) || (len[0] == 1 && len[1] == 0 && left[0].is_identity()) ||
+                        (len[0] == 0 && len[1] == 1 && left[1].is_identity()) ||
+                        (len[0] == 1 && len[1] == 1 && left[0].x == left[1].x && left[0].y == left[1].y);   // :549-553
+        if (!ok) throw StatusError{EAGEN_E_SUM_NONZERO, "compute_divisor_witness_naive: points do not sum to the identity"};
+        if (nl[0] > cap_pos || nl[1] > cap_neg) throw StatusError{EAGEN_E_LEN, "compute_divisor_witness_naive: line buffers too small"};
+        if (nl[0]) EAGEN_CUDA(cudaMemcpyAsync(pos, lines[0], nl[0] * sizeof(Line), cudaMemcpyDeviceToHost, st_));
+        if (nl[1]) EAGEN_CUDA(cudaMemcpyAsync(neg, lines[1], nl[1] * sizeof(Line), cudaMemcpyDeviceToHost, st_));
+        EAGEN_CUDA(cudaStreamSynchronize(st_));
+        *n_pos = nl[0]; *n_neg = nl[1];
+    }
+
 private:
     struct ProfEntry { std::string name; uint64_t launches = 0, scopes = 0; double ms = 0, bytes = 0, modmul = 0; };
     struct ProfPending { int tag; cudaEvent_t a, b; uint64_t l0, l1; };
@@ -741,6 +837,7 @@ private:
             EAGEN_CUDA(cudaMemset(d_err_, 0, sizeof(int)));
             if (e & KERR_RANGE) throw StatusError{EAGEN_E_RANGE, "scalar out of range: must be < isqrt(order)+2"};
             if (e & KERR_DIGITS) throw StatusError{EAGEN_E_DIGITS, "negbase expansion does not fit in d digits"};
+            if (e & KERR_PSW_SLOT) throw StatusError{EAGEN_E_ARG, "prepare_scalar_witness (faithful mode): limb slot i % logtable + 1 exceeds num_limbs (the reference indexes out of bounds here)"};
             throw StatusError{EAGEN_E_DOMAIN, "an intermediate point's x-coordinate lies on the evaluation domain"};
         }
     }
@@ -829,7 +926,12 @@ private:
 
     void run_negbase(const Fe<FS>* ds, size_t n, const NegbaseParams& prm, uint8_t* planes, uint8_t* rows) {
         Scope ps(this, "negbase", (double)n * (32.0 + prm.d * (rows ? 2.0 : 1.0)), (double)n);
-        launch(k_negbase<FS>, n, 128, ds, n, prm, planes, rows, d_err_);
+        if (n == 0) return;
+        const size_t smem = ((size_t)prm.nw * NEGBASE_THREADS + prm.lut_n) * sizeof(uint32_t);
+        const int vec = (n % 4 == 0) && (((uintptr_t)planes & 3) == 0);
+        k_negbase<FS><<<(unsigned)((n + NEGBASE_THREADS - 1) / NEGBASE_THREADS), NEGBASE_THREADS, smem, st_>>>(ds, n, prm, planes, rows, vec, d_err_);
+        ++launches_;
+        EAGEN_CUDA(cudaGetLastError());
     }
 
     void run_multiples(const F* dp, size_t n, uint8_t base, Aff* tab) {

@@ -104,18 +104,31 @@ __global__ void k_binv_base(Fe<FP>* x, size_t M) {
 
 // ------------------------------------------------------------------------------------------------
 // K1  negabase digits.  x = sum d_i (-b)^i  <=>  the ordinary base-b digits e_i of y = x + K with
-// K = sum_{odd i<d} (b-1) b^i satisfy d_i = e_i (i even), d_i = b-1-e_i (i odd).  One thread per scalar,
-// 128-bit loads, chunked long division by b^c < 2^32.
+// K = sum_{odd i<d} (b-1) b^i satisfy d_i = e_i (i even), d_i = b-1-e_i (i odd).
+//
+// The base-b digits of y are produced WITHOUT any division, most significant first (the order the planes are stored in):
+// G = floor(y * ceil(2^288 / b^d) / 2^128) + 1 is a 160-bit fixed-point image of y / b^d whose error lies in (0, b^-d), so the
+// integer part of G * b^k is exactly floor(y / b^(d-k)) for every k; every step multiplies the fraction by b^g (five
+// 32x32->64 products) and the overflow limb is the value of the next g digits.  Groups of g = 4 (b <= 5), 2 (b <= 31) digits are
+// split with a shared-memory table that already holds the complemented bytes; larger bases pop one digit per step.
+// Four digit positions are packed per 32-bit word, the block transposes the words in shared memory and writes the
+// position-major planes with 32-bit stores of four neighbouring scalars (a warp covers 128 contiguous bytes of four rows).
 // ------------------------------------------------------------------------------------------------
 struct NegbaseParams {
     uint32_t sq[8];      // isqrt(order)+2 (canonical limbs)
     uint32_t K[8];       // offset constant
     uint32_t bd[8];      // b^d
-    uint32_t base, d, chunk_digits, chunk;  // chunk = base^chunk_digits <= 2^15, so (rem << 16 | half-limb) fits 31 bits
-    uint32_t chunk_magic, chunk_shift;      // x / chunk == (x * chunk_magic) >> chunk_shift  for x < 2^31
-    uint32_t base_magic, base_shift;        // x / base  == (x * base_magic)  >> base_shift   for x < 2^31
-    uint8_t tops[32];                       // tops[s] = index of the highest possibly non-zero 16-bit half-limb before step s
+    uint32_t inv[6];     // ceil(2^288 / b^d)  (<= 2^160 because b^d >= 2^128)
+    uint32_t pw[5];      // b^0 .. b^4
+    uint32_t base, d;
+    uint32_t g;          // digits per table group: 4, 2, or 1 (no table)
+    uint32_t lut_n;      // b^g table entries (0 when g == 1)
+    uint32_t nw;         // words of four digit positions: 4*nw = d + pad
+    uint32_t pad;        // leading positions of word 0 that do not exist (their digits are zero)
 };
+
+constexpr int NEGBASE_THREADS = 128;
+constexpr int NEGBASE_MAX_WORDS = 36;   // d <= 144
 
 EAGEN_HD bool lt8(const uint32_t* a, const uint32_t* b) {
     for (int i = 7; i >= 0; --i) {
@@ -124,48 +137,154 @@ EAGEN_HD bool lt8(const uint32_t* a, const uint32_t* b) {
     return false;
 }
 
-// One thread per scalar: two 128-bit loads, Montgomery -> canonical, + K, then short division of 16-bit half-limbs by
-// base^c <= 2^15 with multiply-shift reciprocals (no hardware divide: a 64-bit `div` costs ~100 instructions and made the
-// first version of this kernel integer-bound at 10 % of HBM bandwidth), digits peeled from each chunk the same way.
-// Plane stores are coalesced across the warp (32 consecutive bytes per digit position).
-template <class FS>
-__global__ void k_negbase(const Fe<FS>* __restrict__ scalars, size_t n, NegbaseParams prm, uint8_t* __restrict__ planes /* d x n */,
-                          uint8_t* __restrict__ rows /* n x d or null */, int* err) {
-    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    Fe<FS> x = to_canonical(ldg(scalars + j));
-    if (!lt8(x.v, prm.sq)) { atomicOr(err, KERR_RANGE); return; }
+// Montgomery residue -> canonical integer: eight reduction rows and no products by the operand (a * 1), so the zero and
+// power-of-two limbs of the Pasta moduli fold away at compile time.
+template <class FP>
+EAGEN_HD void from_mont(const uint32_t* a, uint32_t* t) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = a[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint32_t m = t[0] * FP::INV;
+        uint64_t c = (uint64_t)m * FP::mod(0) + t[0];
+        c >>= 32;
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+            c += (uint64_t)m * FP::mod(j) + t[j];
+            t[j - 1] = (uint32_t)c;
+            c >>= 32;
+        }
+        t[7] = (uint32_t)c;
+    }
+    reduce_once<FP>(t, 0);
+}
+
+// table entry for the group value v < b^g: g bytes, most significant digit in byte 0; inside a word of four positions the
+// bytes at even offsets belong to odd digit indices (4 | d + pad) and are stored complemented
+EAGEN_HD uint32_t negbase_lut_entry(uint32_t v, uint32_t base, uint32_t g) {
+    uint32_t w = 0;
+    for (uint32_t k = g; k-- > 0;) {
+        uint32_t e = v % base;
+        v /= base;
+        uint32_t dg = (k & 1) ? e : (base - 1 - e);
+        w |= dg << (8 * k);
+    }
+    return w;
+}
+
+// The NW words (four digit positions each, MSD first, byte 0 = first position) of one scalar's canonical value x.
+// Word w goes to out[w * stride]; `lut` may be null when prm.g == 1.  Returns 0 or a KERR_* flag (words are zeroed then).
+EAGEN_HD int negbase_words(const uint32_t* x, const NegbaseParams& prm, const uint32_t* lut, uint32_t* out, uint32_t stride) {
+    if (!lt8(x, prm.sq)) { for (uint32_t w = 0; w < prm.nw; ++w) out[w * stride] = 0u; return KERR_RANGE; }
     uint32_t y[8];
     uint64_t c = 0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { c += (uint64_t)x.v[i] + prm.K[i]; y[i] = (uint32_t)c; c >>= 32; }
-    if (!lt8(y, prm.bd)) { atomicOr(err, KERR_DIGITS); return; }
-    uint32_t h[16];
+    for (int i = 0; i < 8; ++i) { c += (uint64_t)x[i] + prm.K[i]; y[i] = (uint32_t)c; c >>= 32; }
+    if (!lt8(y, prm.bd)) { for (uint32_t w = 0; w < prm.nw; ++w) out[w * stride] = 0u; return KERR_DIGITS; }
+    // y < b^d < 2^143: five limbs.  P = y * inv < 2^288 (limbs 9 and 10 end up zero), G = P[4..8] + 1
+    uint32_t P[11];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { h[2 * i] = y[i] & 0xffffu; h[2 * i + 1] = y[i] >> 16; }
-    const uint32_t d = prm.d, base = prm.base;
-    uint32_t i = 0;
-    for (int step = 0; i < d; ++step) {
-        const int top = prm.tops[step];   // host-computed bound, uniform across the grid: h[] stays in registers
-        uint32_t rem = 0;
+    for (int i = 0; i < 11; ++i) P[i] = 0;
 #pragma unroll
-        for (int l = 15; l >= 0; --l) {
-            if (l <= top) {
-                uint32_t cur = (rem << 16) | h[l];
-                uint32_t q = (uint32_t)(((uint64_t)cur * prm.chunk_magic) >> prm.chunk_shift);
-                rem = cur - q * prm.chunk;
-                h[l] = q;
+    for (int i = 0; i < 5; ++i) {
+        uint64_t cy = 0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            cy += (uint64_t)y[i] * prm.inv[j] + P[i + j];
+            P[i + j] = (uint32_t)cy;
+            cy >>= 32;
+        }
+        P[i + 6] = (uint32_t)cy;
+    }
+    uint32_t G[5];
+    c = 1;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) { c += P[4 + i]; G[i] = (uint32_t)c; c >>= 32; }
+    const uint32_t g = prm.g, base = prm.base, slots = 4 / g;
+    for (uint32_t w = 0; w < prm.nw; ++w) {
+        uint32_t word = 0;
+        for (uint32_t s = 0; s < slots; ++s) {
+            // positions 4w + s*g .. + g-1 of the padded expansion; r of them exist
+            int r = (int)(4 * w + (s + 1) * g) - (int)prm.pad;
+            r = r < 0 ? 0 : (r > (int)g ? (int)g : r);
+            uint32_t v = 0;
+            if (r > 0) {
+                const uint32_t m = prm.pw[r];
+                uint64_t cy = 0;
+#pragma unroll
+                for (int l = 0; l < 5; ++l) { cy += (uint64_t)G[l] * m; G[l] = (uint32_t)cy; cy >>= 32; }
+                v = (uint32_t)cy;
+            }
+            uint32_t bytes;
+            if (g == 1) bytes = (s & 1) ? v : (base - 1 - v);
+            else bytes = lut[v];
+            word |= bytes << (8 * g * s);
+        }
+        out[w * stride] = word;
+    }
+    return 0;
+}
+
+// One thread per scalar for the arithmetic, then a block-wide transpose through shared memory (see the header above).
+// vec != 0: n % 4 == 0 and the planes are 4-byte aligned, so the 32-bit plane stores are legal; otherwise bytes are stored.
+template <class FS>
+__global__ void __launch_bounds__(NEGBASE_THREADS)
+k_negbase(const Fe<FS>* __restrict__ scalars, size_t n, NegbaseParams prm, uint8_t* __restrict__ planes /* d x n */,
+          uint8_t* __restrict__ rows /* n x d or null */, int vec, int* err) {
+    extern __shared__ uint32_t nb_sm[];
+    uint32_t* W = nb_sm;                                   // nw x NEGBASE_THREADS words
+    uint32_t* lut = nb_sm + prm.nw * NEGBASE_THREADS;      // lut_n entries
+    for (uint32_t v = threadIdx.x; v < prm.lut_n; v += NEGBASE_THREADS) lut[v] = negbase_lut_entry(v, prm.base, prm.g);
+    __syncthreads();
+    const size_t j0 = (size_t)blockIdx.x * NEGBASE_THREADS;
+    const size_t j = j0 + threadIdx.x;
+    if (j < n) {
+        Fe<FS> xm = ldg(scalars + j);
+        uint32_t x[8];
+        from_mont<FS>(xm.v, x);
+        int e = negbase_words(x, prm, lut, W + threadIdx.x, NEGBASE_THREADS);
+        if (e) atomicOr(err, e);
+    } else {
+        for (uint32_t w = 0; w < prm.nw; ++w) W[w * NEGBASE_THREADS + threadIdx.x] = 0;
+    }
+    __syncthreads();
+    const uint32_t d = prm.d, pad = prm.pad;
+    if (vec) {
+        const uint32_t quads = NEGBASE_THREADS / 4;
+        for (uint32_t it = threadIdx.x; it < prm.nw * quads; it += NEGBASE_THREADS) {
+            const uint32_t w = it / quads, q = it - w * quads;
+            const size_t jq = j0 + 4 * q;
+            if (jq >= n) continue;
+            const uint4 xw = *reinterpret_cast<const uint4*>(W + w * NEGBASE_THREADS + 4 * q);
+            // 4 x 4 byte transpose: o[k] = byte k of the four scalars' words
+            const uint32_t t0 = __byte_perm(xw.x, xw.y, 0x5140), t1 = __byte_perm(xw.z, xw.w, 0x5140);
+            const uint32_t t2 = __byte_perm(xw.x, xw.y, 0x7362), t3 = __byte_perm(xw.z, xw.w, 0x7362);
+            const uint32_t o[4] = {__byte_perm(t0, t1, 0x5410), __byte_perm(t0, t1, 0x7632), __byte_perm(t2, t3, 0x5410), __byte_perm(t2, t3, 0x7632)};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int pos = (int)(4 * w + k) - (int)pad;
+                if (pos >= 0) *reinterpret_cast<uint32_t*>(planes + (size_t)pos * n + jq) = o[k];
             }
         }
-        uint32_t r = rem;
-        for (uint32_t k = 0; k < prm.chunk_digits && i < d; ++k, ++i) {
-            uint32_t q = (uint32_t)(((uint64_t)r * prm.base_magic) >> prm.base_shift);
-            uint32_t e = r - q * base;
-            r = q;
-            uint32_t dg = (i & 1) ? (base - 1 - e) : e;
-            uint32_t pos = d - 1 - i;  // MSD first
-            planes[(size_t)pos * n + j] = (uint8_t)dg;
-            if (rows) rows[j * d + pos] = (uint8_t)dg;
+    } else {
+        for (uint32_t it = threadIdx.x; it < prm.nw * NEGBASE_THREADS; it += NEGBASE_THREADS) {
+            const uint32_t w = it / NEGBASE_THREADS, t = it - w * NEGBASE_THREADS;
+            if (j0 + t >= n) continue;
+            const uint32_t word = W[w * NEGBASE_THREADS + t];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int pos = (int)(4 * w + k) - (int)pad;
+                if (pos >= 0) planes[(size_t)pos * n + j0 + t] = (uint8_t)(word >> (8 * k));
+            }
+        }
+    }
+    if (rows && j < n) {
+        for (uint32_t w = 0; w < prm.nw; ++w) {
+            const uint32_t word = W[w * NEGBASE_THREADS + threadIdx.x];
+            for (int k = 0; k < 4; ++k) {
+                const int pos = (int)(4 * w + k) - (int)pad;
+                if (pos >= 0) rows[j * d + pos] = (uint8_t)(word >> (8 * k));
+            }
         }
     }
 }
@@ -976,6 +1095,124 @@ __global__ void k_eval_function(const Fe<FP>* __restrict__ A, int la, const Fe<F
     for (int i = la - 1; i >= 0; --i) va = add(mul(va, p.x), ldg(A + i));
     for (int i = lb - 1; i >= 0; --i) vb = add(mul(vb, p.x), ldg(B + i));
     stg(out + j, add(va, mul(vb, p.y)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// prepare_scalar_witness on the digit planes (reference: src/negbase_utils.rs:79-124): per scalar, base rows of
+// (num_limbs + 1) entries -- Entry::Scalar at (0,0), Entry::Bucket(sum of (-b)^i over the positions holding digit r) at (r,0),
+// Entry::Limb(value, bitmask) elsewhere.  i128 arithmetic wraps like a release build of the reference.
+//   mode 0 (faithful): a non-zero digit at position i lands in slot i % logtable + 1 with exponent i % logtable (:98-101)
+//   mode 1 (intended): slot i / logtable + 1, exponent i % logtable
+// One thread per (scalar, row); the digit planes are read coalesced across scalars; HBM-bound, no field arithmetic.
+// ------------------------------------------------------------------------------------------------
+struct PswEntry { uint64_t lo, hi; uint32_t mask, kind; uint64_t zero; };   // 32 bytes; kind: 0 Scalar, 1 Bucket, 2 Limb
+enum : int { KERR_PSW_SLOT = 8 };   // faithful mode: limb slot beyond num_limbs (the reference's out-of-bounds panic)
+
+struct W128 { uint64_t lo, hi; };
+EAGEN_HD W128 w128_add(W128 a, W128 b) { W128 r; r.lo = a.lo + b.lo; r.hi = a.hi + b.hi + (r.lo < a.lo ? 1u : 0u); return r; }
+EAGEN_HD W128 w128_mul_small(W128 a, uint32_t b) {
+    const uint64_t M = 0xffffffffull;
+    uint64_t p0 = (a.lo & M) * b, p1 = (a.lo >> 32) * b + (p0 >> 32);
+    W128 r; r.lo = (p1 << 32) | (p0 & M); r.hi = a.hi * b + (p1 >> 32);
+    return r;
+}
+EAGEN_HD W128 w128_neg(W128 a) { W128 r; r.lo = ~a.lo + 1; r.hi = ~a.hi + (r.lo == 0 ? 1u : 0u); return r; }
+
+template <class FS>
+__global__ void k_scalar_witness(const uint8_t* __restrict__ planes /* d x n, MSD first */, size_t n, uint32_t d, uint32_t base,
+                                 uint32_t num_digits, uint32_t logtable, uint32_t num_limbs, int mode,
+                                 const Fe<FS>* __restrict__ scalars, PswEntry* __restrict__ out, int* err) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = blockIdx.y;
+    if (j >= n) return;
+    const uint32_t cols = num_limbs + 1;
+    PswEntry* o = out + ((size_t)j * base + r) * cols;
+    auto digit = [&](uint32_t i) -> uint32_t { return planes[(size_t)(d - 1 - i) * n + j]; };
+    auto match = [&](uint32_t dg) -> bool { return r == 0 ? dg != 0 : dg == r; };
+    PswEntry e0;
+    e0.zero = 0; e0.mask = 0;
+    if (r == 0) {
+        uint32_t x[8];
+        Fe<FS> xm = ldg(scalars + j);
+        from_mont<FS>(xm.v, x);
+        e0.lo = (uint64_t)x[0] | ((uint64_t)x[1] << 32); e0.hi = (uint64_t)x[2] | ((uint64_t)x[3] << 32); e0.kind = 0;
+        int bad = 0;
+        for (uint32_t i = 0; i < d; ++i) {
+            if (digit(i) == 0) continue;
+            if (i >= num_digits) bad |= KERR_DIGITS;                               // assert!(digits.len() <= num_digits)  :81
+            if (mode == 0 && (i % logtable) >= num_limbs) bad |= KERR_PSW_SLOT;    // ret[..][i % logtable + 1] out of bounds
+        }
+        if (bad) atomicOr(err, bad);
+    } else {
+        W128 acc = {0, 0}, pw = {1, 0};
+        for (uint32_t i = 0; i < d; ++i) {
+            if (digit(i) == r) acc = w128_add(acc, pw);
+            pw = w128_neg(w128_mul_small(pw, base));
+        }
+        e0.lo = acc.lo; e0.hi = acc.hi; e0.kind = 1;
+    }
+    o[0] = e0;
+    for (uint32_t e = 1; e <= num_limbs; ++e) {
+        W128 acc = {0, 0};
+        uint32_t mask = 0;
+        if (mode == 0) {
+            const uint32_t k0 = e - 1;   // the only exponent that reaches slot e
+            if (k0 < logtable) {
+                uint32_t cnt = 0;
+                for (uint32_t i = k0; i < d; i += logtable) cnt += match(digit(i)) ? 1u : 0u;
+                W128 pw = {1, 0};
+                for (uint32_t k = 0; k < k0; ++k) pw = w128_neg(w128_mul_small(pw, base));
+                acc = w128_mul_small(pw, cnt);
+                mask = cnt << k0;
+            }
+        } else {
+            W128 pw = {1, 0};
+            for (uint32_t k = 0; k < logtable; ++k) {
+                const uint32_t i = (e - 1) * logtable + k;
+                if (i < d && match(digit(i))) { acc = w128_add(acc, pw); mask += 1u << k; }
+                pw = w128_neg(w128_mul_small(pw, base));
+            }
+        }
+        PswEntry en;
+        en.lo = acc.lo; en.hi = acc.hi; en.mask = mask; en.kind = 2; en.zero = 0;
+        o[e] = en;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute_divisor_witness_naive (reference: src/regular_functions_utils.rs:483-551): one round joins the pairs the host
+// planned from the identity flags of the current list; pair t of the round (in the reference's push order) produces the line
+// through (a, b) and the point -(a + b), both stored at the reference's pop order np - 1 - t.
+// ------------------------------------------------------------------------------------------------
+template <class FP>
+__global__ void k_identity_flags(const Affine<FP>* __restrict__ pts, size_t m, uint8_t* __restrict__ flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) flags[i] = ldg_aff(pts + i).is_identity() ? 1 : 0;
+}
+template <class FP>
+__global__ void k_naive_den(const Affine<FP>* __restrict__ list, const int2* __restrict__ pairs, size_t np, Fe<FP>* __restrict__ den) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= np) return;
+    int2 pr = pairs[t];
+    stg(den + t, pair_den(ldg_aff(list + pr.x), ldg_aff(list + pr.y)));
+}
+template <class FP>
+struct LineTriple { Fe<FP> lx, ly, lz; };
+template <class FP>
+__global__ void k_naive_finish(const Affine<FP>* __restrict__ list, const int2* __restrict__ pairs, size_t np, const Fe<FP>* __restrict__ dinv,
+                               Affine<FP>* __restrict__ next /* np slots */, LineTriple<FP>* __restrict__ lines /* np slots */) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= np) return;
+    int2 pr = pairs[t];
+    Affine<FP> a = ldg_aff(list + pr.x), b = ldg_aff(list + pr.y);
+    Affine<FP> c = aneg(pair_sum(a, b, ldg(dinv + t)));
+    LineTriple<FP> l;
+    // a is never the identity (the reference skips it, :517); b may be: the cross product then vanishes and linefunc falls back
+    // to the line through a and -(a + O) = -a (:296-302)
+    line_coeffs(a, b.is_identity() ? aneg(a) : b, c, l.lx, l.ly, l.lz);
+    const size_t o = np - 1 - t;
+    stg_aff(next + o, c);
+    stg(&lines[o].lx, l.lx); stg(&lines[o].ly, l.ly); stg(&lines[o].lz, l.lz);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -137,6 +137,26 @@ void eagen_result_free(eagen_result* r);
  * scalars: n x 32 B Montgomery (scalar field); pts: n Jacobian points; out: affine (64 B).  device_ms may be NULL. */
 int eagen_msm(eagen_ctx* ctx, const uint64_t* scalars, const uint64_t* pts, size_t n, uint64_t* out_affine, double* device_ms);
 
+/* prepare_scalar_witness for n scalars     src/negbase_utils.rs:39-43,79-124
+ * scalars: n x 32 B Montgomery (scalar field).  out: n x base x (num_limbs + 1) entries, num_limbs = ceil(num_digits / logtable),
+ * row-major [scalar][row][slot]; one entry = 32 bytes:
+ *     u64 value_lo | u64 value_hi (two's complement i128; Entry::Scalar: the canonical scalar) | u32 bitmask | u32 kind | 8 zero bytes
+ *     kind: 0 = Entry::Scalar (row 0, slot 0), 1 = Entry::Bucket (row r >= 1, slot 0), 2 = Entry::Limb (slot >= 1)
+ * mode EAGEN_PSW_FAITHFUL follows the reference as written (limb slot i % logtable + 1, :98-101; EAGEN_E_ARG where the reference
+ * indexes out of bounds), EAGEN_PSW_INTENDED uses slot i / logtable + 1.  i128 sums wrap (release-build semantics of the reference).
+ * Errors: EAGEN_E_RANGE (scalar >= isqrt(order)+2), EAGEN_E_DIGITS (more than num_digits digits, the assert at :81). */
+enum eagen_psw_mode { EAGEN_PSW_FAITHFUL = 0, EAGEN_PSW_INTENDED = 1 };
+int eagen_prepare_scalar_witness(eagen_ctx* ctx, const uint64_t* scalars, size_t n, uint8_t base, uint32_t num_digits,
+                                 uint32_t logtable, int mode, void* out, size_t out_bytes);
+
+/* compute_divisor_witness_naive: the witness as an Arrangement of numerator (pos) and denominator (neg) lines
+ *                                 src/regular_functions_utils.rs:483-551
+ * pts: n Jacobian points summing to the identity (EAGEN_E_SUM_NONZERO otherwise).  A line is lx | ly | lz (96 bytes):
+ * RegularFunction::from_line(lx, ly, lz), i.e. a = [lz, lx], b = [ly]; lines appear in the reference's push order.
+ * *n_pos / *n_neg: capacity of the buffers in lines on entry (n each always suffices), number of lines on return. */
+int eagen_divisor_witness_naive(eagen_ctx* ctx, const uint64_t* pts, size_t n, uint64_t* pos_lines, size_t* n_pos,
+                                uint64_t* neg_lines, size_t* n_neg);
+
 /* ---- helper API of regular_functions_utils ------------------------------------------------------------ */
 
 /* &Polynomial * &Polynomial                                   src/regular_functions_utils.rs:209-216

@@ -19,8 +19,12 @@ int eagen_selftest_field(int field, int op, const uint64_t* a, const uint64_t* b
 /* op: 0 complete add (p, q Jacobian), 1 double p, 2 mixed add (q must be z = 1), 3 small multiple k*p.
  * Inputs are Jacobian (96 B); out is affine (64 B), identity = zeros. */
 int eagen_selftest_curve(int curve, int op, const uint64_t* p, const uint64_t* q, uint32_t k, uint64_t* out_affine);
-/* K1 constants for (curve, base): d, chunk, chunk_digits, and the limbs sq | K | b^d (3 x 32 bytes) */
-int eagen_selftest_negbase_params(int curve, uint8_t base, uint32_t* d, uint32_t* chunk, uint32_t* chunk_digits, uint32_t* limbs24);
+/* K1 constants for (curve, base): d, digits per table group, words of four positions, and the limbs
+ * sq | K | b^d | ceil(2^288 / b^d) (4 x 32 bytes) */
+int eagen_selftest_negbase_params(int curve, uint8_t base, uint32_t* d, uint32_t* group, uint32_t* words, uint32_t* limbs32);
+/* K1's per-scalar arithmetic (Montgomery -> canonical, division-free digit extraction, complement table) on the host:
+ * d digits, most significant first, of one Montgomery scalar; *kerr = 0, 1 (range) or 2 (more than d digits) */
+int eagen_selftest_negbase_digits(int curve, uint8_t base, const uint64_t* scalar, uint8_t* digits, int* kerr);
 /* the pass plan of a 2^t transform: writes up to 8 (s_hi, s_lo) pairs, returns the count */
 int eagen_selftest_ntt_plan(int t, int* pairs16);
 #ifdef __cplusplus

@@ -181,6 +181,19 @@ template <class C> int eval_fn(const u64* a, size_t la, const u64* b, size_t lb,
     }
 #define GUARD(BODY) try { BODY; return 0; } catch (const std::exception& e) { g_err = e.what(); return -1; }
 
+// compute_divisor_witness_naive: lines as lx | ly | lz (12 x u64 each); *n_pos / *n_neg carry the capacities in, counts out
+template <class C> void run_naive(const u64* pts, size_t n, u64* pos, size_t* n_pos, u64* neg, size_t* n_neg) {
+    Arrangement<C> a = compute_divisor_witness_naive<C>(unpack_points<C>(pts, n));
+    if (a.pos.size() > *n_pos || a.neg.size() > *n_neg) throw std::runtime_error("line buffers too small");
+    auto put = [](const std::vector<typename Arrangement<C>::Line>& v, u64* out) {
+        for (size_t i = 0; i < v.size(); ++i) {
+            std::memcpy(out + 12 * i, v[i].lx.v, 32); std::memcpy(out + 12 * i + 4, v[i].ly.v, 32); std::memcpy(out + 12 * i + 8, v[i].lz.v, 32);
+        }
+    };
+    put(a.pos, pos); put(a.neg, neg);
+    *n_pos = a.pos.size(); *n_neg = a.neg.size();
+}
+
 extern "C" {
 
 const char* oracle_last_error() { return g_err.c_str(); }
@@ -221,6 +234,21 @@ int oracle_lhs_witness(int curve, const u64* scalars, const u64* pts, size_t n, 
 }
 int oracle_divisor_witness(int curve, const u64* pts, size_t n, int partial, u64* out_point, void** handle) {
     GUARD(DISPATCH_CURVE(curve, *handle = run_divisor<C>(pts, n, partial, out_point)))
+}
+// prepare_scalar_witness: `mag` = canonical scalar (4 x u64); out = base * (num_limbs+1) entries of 32 bytes:
+// value (u64 lo, u64 hi: two's complement i128) | u32 mask | u32 kind (0 Scalar, 1 Bucket, 2 Limb) | 8 zero bytes
+int oracle_prepare_scalar_witness(const u64* mag, uint8_t base, size_t num_digits, size_t logtable, int mode, u64* out) {
+    GUARD({
+        U256 m; std::memcpy(m.w, mag, 32);
+        std::vector<PswEntry> v = prepare_scalar_witness(m, base, num_digits, logtable, mode);
+        for (size_t i = 0; i < v.size(); ++i) {
+            out[4 * i] = (u64)v[i].value; out[4 * i + 1] = (u64)(v[i].value >> 64);
+            out[4 * i + 2] = (u64)v[i].mask | ((u64)v[i].kind << 32); out[4 * i + 3] = 0;
+        }
+    })
+}
+int oracle_divisor_witness_naive(int curve, const u64* pts, size_t n, u64* pos, size_t* n_pos, u64* neg, size_t* n_neg) {
+    GUARD(DISPATCH_CURVE(curve, run_naive<C>(pts, n, pos, n_pos, neg, n_neg)))
 }
 void oracle_result_free(void* h) { delete (ResultBase*)h; }
 unsigned oracle_result_d(void* h) { return ((ResultBase*)h)->d; }

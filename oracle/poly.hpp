@@ -347,6 +347,53 @@ RegularFunction<C> compute_divisor_witness(const std::vector<Point<C>>& pts) {
     return tmp.first;
 }
 
+// compute_divisor_witness_naive  (reference: :483-551): the witness as an arrangement of numerator and denominator lines.
+// Lines are kept as (lx, ly, lz) triples (RegularFunction::from_line(lx, ly, lz): a = [lz, lx], b = [ly]).  Oracle convention
+// as everywhere: every point handed to linefunc is z = 1 normalised.
+template <class C>
+struct Arrangement {
+    typedef typename Point<C>::F F;
+    struct Line { F lx, ly, lz; };
+    std::vector<Line> pos, neg;
+};
+template <class C>
+Arrangement<C> compute_divisor_witness_naive(const std::vector<Point<C>>& pts) {
+    typedef typename Arrangement<C>::Line Line;
+    std::vector<Point<C>> pos(pts.size()), neg;
+    for (size_t i = 0; i < pts.size(); ++i) pos[i] = pts[i].normalized();
+    Arrangement<C> ret;
+    struct Glue { Point<C> a, b, sum; Line line; };
+    std::vector<Glue> tmp;
+    auto f = [&](std::vector<Glue>& v) {  // :497-504  q = a + b; Out(linefunc(a, b), -q)
+        Pool::instance().parallel_for(v.size(), [&](size_t lo, size_t hi) {
+            for (size_t k = lo; k < hi; ++k) {
+                RegularFunction<C> l = linefunc<C>(v[k].a, v[k].b);
+                v[k].line.lz = l.a.poly[0]; v[k].line.lx = l.a.poly[1]; v[k].line.ly = l.b.poly[0];
+                v[k].sum = (-(v[k].a + v[k].b)).normalized();
+            }
+        });
+    };
+    auto drain = [&](std::vector<Point<C>>& from) {  // :515-520 / :531-536
+        while (from.size() > 1) {
+            Point<C> inc1 = from.back(); from.pop_back();
+            if (!inc1.is_identity()) { Glue g; g.a = inc1; g.b = from.back(); from.pop_back(); tmp.push_back(g); }
+        }
+    };
+    while (pos.size() > 1 || neg.size() > 1) {  // :513
+        drain(pos);
+        f(tmp);
+        while (!tmp.empty()) { ret.pos.push_back(tmp.back().line); neg.push_back(tmp.back().sum); tmp.pop_back(); }  // :523-529
+        drain(neg);
+        f(tmp);
+        while (!tmp.empty()) { ret.neg.push_back(tmp.back().line); pos.push_back(tmp.back().sum); tmp.pop_back(); }  // :539-545
+    }
+    bool ok = (pos.empty() && neg.empty()) || (pos.size() == 1 && neg.empty() && pos[0].is_identity()) ||
+              (pos.empty() && neg.size() == 1 && neg[0].is_identity()) ||
+              (pos.size() == 1 && neg.size() == 1 && pos[0] == neg[0]);  // :549-553
+    if (!ok) throw std::runtime_error("compute_divisor_witness_naive: points do not sum to identity");
+    return ret;
+}
+
 // Canonical form: trailing zeros stripped, then both polynomials divided by
 // the coefficient of the term of highest pole order (x^i has order 2i, y x^i has order 2i+3).
 template <class C>

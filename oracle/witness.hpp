@@ -95,6 +95,48 @@ Fe<P> table_entry_by_id(uint8_t base, size_t id) {
     return acc;
 }
 
+// prepare_scalar_witness  (reference: src/negbase_utils.rs:39-43,79-124)
+// Returns base x (num_limbs + 1) entries, row-major.  Entry (0,0) is Entry::Scalar, (i,0) for i >= 1 Entry::Bucket(i128),
+// (i,j) for j >= 1 Entry::Limb(i128, u32).  The reference accumulates in i128 / u32; (-base)^i overflows i128 for long
+// expansions of small bases (debug build: panic, release build: wrap) -- the oracle wraps (two's complement, mod 2^128).
+//   mode 0 = faithful: limb slot i % logtable + 1 and exponent i % logtable exactly as written (:98-101); a slot beyond
+//            num_limbs is the reference's out-of-bounds panic and throws here
+//   mode 1 = intended: limb slot i / logtable + 1, exponent i % logtable
+struct PswEntry {
+    unsigned __int128 value = 0;   // two's complement i128 (Scalar: the canonical scalar)
+    uint32_t mask = 0;
+    uint32_t kind = 0;             // 0 Scalar, 1 Bucket, 2 Limb
+};
+inline std::vector<PswEntry> prepare_scalar_witness(const U256& sc, uint8_t base, size_t num_digits, size_t logtable, int mode) {
+    typedef unsigned __int128 u128w;
+    if (base < 2 || logtable == 0) throw std::runtime_error("prepare_scalar_witness: bad base / logtable");
+    std::vector<uint8_t> digits = negbase_decompose(sc, false, base);
+    if (digits.size() > num_digits) throw std::runtime_error("prepare_scalar_witness: more than num_digits digits");  // :81
+    size_t num_limbs = (num_digits + logtable - 1) / logtable;  // :82
+    size_t cols = num_limbs + 1;
+    std::vector<PswEntry> ret((size_t)base * cols);
+    auto negpow = [&](size_t e) { u128w r = 1; for (size_t k = 0; k < e; ++k) r = (u128w)0 - r * base; return r; };  // (-base)^e
+    for (size_t i = 0; i < digits.size(); ++i) {  // :93-105
+        if (digits[i] == 0) continue;             // id_by_digit -> None
+        size_t row = digits[i];                   // id + 1
+        size_t slot = (mode == 0 ? i % logtable : i / logtable) + 1, e = i % logtable;
+        if (slot > num_limbs) throw std::runtime_error("prepare_scalar_witness: limb slot out of bounds (reference panics)");
+        ret[row * cols + 0].value += negpow(i);
+        ret[row * cols + slot].value += negpow(e);
+        ret[row * cols + slot].mask += (uint32_t)1 << e;
+        ret[0 * cols + slot].value += negpow(e);
+        ret[0 * cols + slot].mask += (uint32_t)1 << e;
+    }
+    for (size_t i = 0; i < base; ++i)  // :109-121
+        for (size_t j = 0; j < cols; ++j) {
+            PswEntry& en = ret[i * cols + j];
+            if (i == 0 && j == 0) { en.kind = 0; en.value = ((u128w)sc.w[1] << 64) | sc.w[0]; en.mask = 0; }
+            else if (j == 0) { en.kind = 1; en.mask = 0; }
+            else en.kind = 2;
+        }
+    return ret;
+}
+
 template <class C>
 struct LhsWitness {
     unsigned d = 0;

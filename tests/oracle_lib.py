@@ -220,3 +220,31 @@ def divisor_witness(curve_id, pts, partial=False):
     r = Result(h, len(pts), with_digits=False)
     r.output = out_pt
     return r
+
+
+def prepare_scalar_witness(sc, base, num_digits, logtable, mode=0):
+    """oracle restatement of src/negbase_utils.rs:79-124 -> rows[base][num_limbs+1] like pyref.prepare_scalar_witness"""
+    w = np.array([(sc >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+    num_limbs = (num_digits + logtable - 1) // logtable
+    out = np.zeros((base, num_limbs + 1, 4), dtype=np.uint64)
+    _chk(lib().oracle_prepare_scalar_witness(_p64(w), C.c_uint8(base), C.c_size_t(num_digits), C.c_size_t(logtable), int(mode), _p64(out)))
+    rows = []
+    for i in range(base):
+        row = []
+        for j in range(num_limbs + 1):
+            v = int(out[i, j, 0]) | (int(out[i, j, 1]) << 64)
+            mask, kind = int(out[i, j, 2]) & 0xFFFFFFFF, int(out[i, j, 2]) >> 32
+            sv = v - (1 << 128) if v >> 127 else v
+            row.append(("scalar", v) if kind == 0 else (("bucket", sv) if kind == 1 else ("limb", sv, mask)))
+        rows.append(row)
+    return rows
+
+
+def divisor_witness_naive(curve_id, pts):
+    """oracle restatement of src/regular_functions_utils.rs:483-551 -> (pos, neg) arrays (k, 3, 4): lx | ly | lz"""
+    pts = np.ascontiguousarray(pts, dtype=np.uint64)
+    n = len(pts)
+    pos, neg = np.zeros((max(n, 1), 3, 4), dtype=np.uint64), np.zeros((max(n, 1), 3, 4), dtype=np.uint64)
+    npos, nneg = C.c_size_t(len(pos)), C.c_size_t(len(neg))
+    _chk(lib().oracle_divisor_witness_naive(curve_id, _p64(pts), C.c_size_t(n), _p64(pos), C.byref(npos), _p64(neg), C.byref(nneg)))
+    return pos[: npos.value], neg[: nneg.value]

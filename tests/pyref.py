@@ -209,6 +209,75 @@ def divisor_witness(pts, cv):
     return f
 
 
+def divisor_witness_naive(pts, cv):
+    """reference: src/regular_functions_utils.rs:483-551; lines as (lx, ly, lz)"""
+    pos, neg, rpos, rneg, tmp = list(pts), [], [], [], []
+
+    def drain(lst):
+        while len(lst) > 1:
+            inc1 = lst.pop()
+            if inc1 is not None:
+                tmp.append((inc1, lst.pop()))
+
+    def flush(lines, sums):
+        out = []
+        for a, b in tmp:
+            la, lb = linefunc(a, b, cv)
+            out.append(((la[1], lb[0], la[0]), cv.neg(cv.add(a, b))))
+        tmp.clear()
+        while out:
+            line, s = out.pop()
+            lines.append(line)
+            sums.append(s)
+
+    while len(pos) > 1 or len(neg) > 1:
+        drain(pos)
+        flush(rpos, neg)
+        drain(neg)
+        flush(rneg, pos)
+    ok = (not pos and not neg) or (len(pos) == 1 and not neg and pos[0] is None) or (not pos and len(neg) == 1 and neg[0] is None) \
+        or (len(pos) == 1 and len(neg) == 1 and pos[0] == neg[0])
+    assert ok, "points do not sum to identity"
+    return rpos, rneg
+
+
+def _wrap_i128(v):
+    v &= (1 << 128) - 1
+    return v - (1 << 128) if v >> 127 else v
+
+
+def prepare_scalar_witness(sc, base, num_digits, logtable, intended=False):
+    """reference: src/negbase_utils.rs:79-124.  Returns rows[base][num_limbs+1] of ("scalar", sc) / ("bucket", v) / ("limb", v, mask);
+    i128 sums wrap (release-build semantics); intended=True uses limb slot i // logtable + 1 instead of i % logtable + 1"""
+    digits = negbase_decompose(sc, base)
+    assert len(digits) <= num_digits
+    num_limbs = (num_digits + logtable - 1) // logtable
+    ret = [[[0, 0] for _ in range(num_limbs + 1)] for _ in range(base)]
+    for i, dg in enumerate(digits):
+        if dg == 0:
+            continue
+        slot = (i // logtable if intended else i % logtable) + 1
+        e = i % logtable
+        if slot > num_limbs:
+            raise IndexError("limb slot out of bounds")
+        ret[dg][0][0] += (-base) ** i
+        for row in (dg, 0):
+            ret[row][slot][0] += (-base) ** e
+            ret[row][slot][1] += 2 ** e
+    out = []
+    for i in range(base):
+        row = []
+        for j in range(num_limbs + 1):
+            if i == 0 and j == 0:
+                row.append(("scalar", sc))
+            elif j == 0:
+                row.append(("bucket", _wrap_i128(ret[i][j][0])))
+            else:
+                row.append(("limb", _wrap_i128(ret[i][j][0]), ret[i][j][1] & 0xFFFFFFFF))
+        out.append(row)
+    return out
+
+
 def lhs_witness(scalars, pts, base, cv):
     """scalars: canonical ints; pts: affine tuples / None.  Returns (digits, carries, fns)."""
     assert len(scalars) == len(pts)

@@ -99,7 +99,8 @@ def test_host_complete_curve_formulas_match_oracle(eagen, oracle, cname):
 
 
 def test_negbase_constants(eagen):
-    """K1's offset trick: digits of x in base -b = base-b digits of x + K with odd positions complemented"""
+    """K1's offset trick: digits of x in base -b = base-b digits of x + K with odd positions complemented; and the
+    fixed-point reciprocal that replaces every division"""
     for cname in ("pallas", "grumpkin"):
         cv = pyref.Curve(cname)
         for base in (2, 3, 5, 17, 255):
@@ -107,7 +108,8 @@ def test_negbase_constants(eagen):
             d = pyref.num_digits(cv, base)
             assert prm["d"] == d and prm["sq"] == pyref.isqrt(cv.q) + 2
             assert prm["K"] == sum((base - 1) * base ** i for i in range(1, d, 2)) and prm["bd"] == base ** d
-            assert prm["chunk"] == base ** prm["chunk_digits"] <= 2 ** 15 < prm["chunk"] * base
+            assert prm["inv"] == -(-(1 << 288) // base ** d) and prm["bd"] < 1 << 143
+            assert prm["words"] == (d + 3) // 4 and prm["group"] in (1, 2, 4) and base ** prm["group"] <= 1024
             rng = pyref.SplitMix64(base)
             for _ in range(50):
                 x = rng.next_bits(2) % prm["sq"]
@@ -118,6 +120,31 @@ def test_negbase_constants(eagen):
                 dg = [(base - 1 - e[i]) if i & 1 else e[i] for i in range(d)]
                 ref = pyref.negbase_decompose(x, base)
                 assert dg == ref + [0] * (d - len(ref))
+
+
+def test_negbase_kernel_arithmetic_on_host(eagen, oracle):
+    """the kernel's own per-scalar source (Montgomery -> canonical, division-free digit extraction, complement table) run on
+    the host against the independent big-int negbase_decompose: every base, edge scalars and random ones"""
+    for cname in ("pallas", "vesta", "grumpkin"):
+        cv = pyref.Curve(cname)
+        sq = pyref.isqrt(cv.q) + 2
+        rng = pyref.SplitMix64(hash(cname) & 0xffff)
+        for base in list(range(2, 40)) + [63, 64, 100, 127, 128, 200, 254, 255]:
+            d = pyref.num_digits(cv, base)
+            xs = [0, 1, 2, base - 1, base, base + 1, base ** 2, sq - 1, sq - 2, (1 << 64) - 1, 1 << 64, base ** (d - 2), base ** (d - 2) - 1]
+            xs += [rng.next_bits(2) % sq for _ in range(12)]
+            for x in xs:
+                if x >= sq:
+                    continue
+                ref = pyref.negbase_decompose(x, base)
+                got, kerr = eagen.selftest_negbase_digits(cv.id, base, oracle.pack_felts([x], cv.q)[0])
+                if len(ref) > d:
+                    assert kerr == 2
+                    continue
+                assert kerr == 0 and list(got) == ([0] * (d - len(ref)) + ref[::-1]), (cname, base, x)
+        # out of range: >= isqrt(order) + 2
+        _, kerr = eagen.selftest_negbase_digits(cv.id, 5, oracle.pack_felts([sq], cv.q)[0])
+        assert kerr == 1
 
 
 def test_ntt_pass_plan(eagen):

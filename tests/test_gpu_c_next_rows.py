@@ -1,0 +1,151 @@
+"""GPU parity tests (pytest -m gpu) for the SURVEY.md section 8f rows next to the hot path, called through the C ABI and
+compared bit for bit with the CPU oracle: prepare_scalar_witness (reference: src/negbase_utils.rs:79-124),
+compute_divisor_witness_naive (src/regular_functions_utils.rs:483-551) and the division-free K1 at every base."""
+import numpy as np
+import pytest
+
+import pyref
+
+pytestmark = pytest.mark.gpu
+CURVES = ["pallas", "vesta", "grumpkin"]
+
+
+def gen_points(cv, n, seed):
+    rng = pyref.SplitMix64(seed)
+    p0, dl = pyref.random_point(rng, cv), pyref.random_point(rng, cv)
+    pts = [p0]
+    for _ in range(n - 1):
+        pts.append(cv.add(pts[-1], dl))
+    return pts
+
+
+def close_sum(pts, cv):
+    s = None
+    for P in pts:
+        s = cv.add(s, P)
+    return pts + [cv.neg(s)]
+
+
+def psw_rows(arr):
+    """structured (base, num_limbs+1) array of one scalar -> the tuple form oracle_lib.prepare_scalar_witness returns"""
+    rows = []
+    for i in range(arr.shape[0]):
+        row = []
+        for j in range(arr.shape[1]):
+            e = arr[i, j]
+            assert int(e["zero"]) == 0
+            v = int(e["lo"]) | (int(e["hi"]) << 64)
+            sv = v - (1 << 128) if v >> 127 else v
+            kind = int(e["kind"])
+            row.append(("scalar", v) if kind == 0 else (("bucket", sv) if kind == 1 else ("limb", sv, int(e["mask"]))))
+        rows.append(row)
+    return rows
+
+
+# ---- K1 at every base -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cname", CURVES)
+def test_negbase_every_base(gpu_ctx, oracle, cname):
+    """digits of edge and random scalars for bases 2..255, ragged n (byte-store path) and n % 4 == 0 (32-bit-store path)"""
+    cv, ctx = pyref.Curve(cname), gpu_ctx(cname)
+    sq = pyref.isqrt(cv.q) + 2
+    rng = pyref.SplitMix64(11)
+    for base in list(range(2, 34)) + [63, 64, 100, 127, 128, 200, 254, 255]:
+        d = pyref.num_digits(cv, base)
+        for n in (131, 260):
+            xs = [0, 1, base - 1, base, sq - 1, sq - 2, (1 << 64) - 1, 1 << 64][: n]
+            xs += [rng.next_bits(2) % sq for _ in range(n - len(xs))]
+            xs = [x for x in xs if len(pyref.negbase_decompose(x, base)) <= d]
+            got = ctx.negbase_decompose(oracle.pack_felts(xs, cv.q), base)
+            assert got.shape == (len(xs), d)
+            for i in list(range(10)) + [len(xs) // 2, len(xs) - 1]:
+                ref = pyref.negbase_decompose(xs[i], base)
+                assert list(got[i]) == [0] * (d - len(ref)) + ref[::-1], (base, n, i)
+
+
+# ---- prepare_scalar_witness --------------------------------------------------------------------------------
+@pytest.mark.parametrize("cname", CURVES)
+@pytest.mark.parametrize("mode", [0, 1])
+def test_prepare_scalar_witness(gpu_ctx, oracle, eagen, cname, mode):
+    cv, ctx = pyref.Curve(cname), gpu_ctx(cname)
+    sq = pyref.isqrt(cv.q) + 2
+    rng = pyref.SplitMix64(900 + mode)
+    for base in (2, 3, 5, 16, 17, 255):
+        d = pyref.num_digits(cv, base)
+        for logtable in (1, 3, 8, 13, 24):
+            num_limbs = (d + logtable - 1) // logtable
+            xs = [0, 1, base, sq - 1] + [rng.next_bits(2) % sq for _ in range(5)]
+            xs = [x for x in xs if len(pyref.negbase_decompose(x, base)) <= d]
+            ok, refs = [], []
+            for x in xs:
+                try:
+                    refs.append(oracle.prepare_scalar_witness(x, base, d, logtable, mode))
+                    ok.append(x)
+                except oracle.OracleError:
+                    # faithful mode: the reference indexes out of bounds -> the product reports EAGEN_E_ARG for the batch
+                    with pytest.raises(eagen.EagenError) as ei:
+                        ctx.prepare_scalar_witness(oracle.pack_felts([x], cv.q), base, d, logtable, mode)
+                    assert ei.value.status == eagen.E_ARG
+            if not ok:
+                continue
+            got = ctx.prepare_scalar_witness(oracle.pack_felts(ok, cv.q), base, d, logtable, mode)
+            assert got.shape == (len(ok), base, num_limbs + 1)
+            for i, ref in enumerate(refs):
+                assert psw_rows(got[i]) == ref, (base, logtable, ok[i])
+
+
+def test_prepare_scalar_witness_batch_and_errors(gpu_ctx, oracle, eagen):
+    """a batch that spans several blocks; the reference's assert on the digit count (:81); empty input"""
+    cv, ctx = pyref.Curve("pallas"), gpu_ctx("pallas")
+    sq = pyref.isqrt(cv.q) + 2
+    rng = pyref.SplitMix64(4)
+    xs = [rng.next_bits(2) % sq for _ in range(1000)]
+    d = pyref.num_digits(cv, 5)
+    got = ctx.prepare_scalar_witness(oracle.pack_felts(xs, cv.q), 5, d, 8, eagen.PSW_INTENDED)
+    for i in (0, 1, 127, 128, 500, 999):
+        assert psw_rows(got[i]) == oracle.prepare_scalar_witness(xs[i], 5, d, 8, 1)
+    with pytest.raises(eagen.EagenError) as ei:   # sq - 1 needs more than 10 digits
+        ctx.prepare_scalar_witness(oracle.pack_felts([sq - 1], cv.q), 5, 10, 8, eagen.PSW_INTENDED)
+    assert ei.value.status == eagen.E_DIGITS
+    with pytest.raises(eagen.EagenError) as ei:
+        ctx.prepare_scalar_witness(oracle.pack_felts([sq], cv.q), 5, d, 8, eagen.PSW_INTENDED)
+    assert ei.value.status == eagen.E_RANGE
+    assert ctx.prepare_scalar_witness(np.zeros((0, 4), np.uint64), 5, d, 8).shape[0] == 0
+
+
+# ---- compute_divisor_witness_naive ---------------------------------------------------------------------------
+@pytest.mark.parametrize("cname", CURVES)
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 8, 33, 100, 1000])
+def test_divisor_witness_naive(gpu_ctx, oracle, cname, n):
+    cv, ctx = pyref.Curve(cname), gpu_ctx(cname)
+    rng = pyref.SplitMix64(n)
+    pts = close_sum(gen_points(cv, n, 3 * n + 1), cv)
+    zs = [rng.next_bits(4) % cv.p or 1 for _ in pts]
+    P = oracle.pack_points(pts, cv.p, zs)
+    pos, neg = ctx.compute_divisor_witness_naive(P)
+    rpos, rneg = oracle.divisor_witness_naive(cv.id, P)
+    assert pos.shape == rpos.shape and (pos == rpos).all()
+    assert neg.shape == rneg.shape and (neg == rneg).all()
+
+
+def test_divisor_witness_naive_degenerate(gpu_ctx, oracle, eagen):
+    cv, ctx = pyref.Curve("pallas"), gpu_ctx("pallas")
+    g = gen_points(cv, 6, 9)
+    cases = [
+        [g[0], None, cv.neg(g[0])],
+        [None, g[0], g[1], None, None, cv.neg(cv.add(g[0], g[1]))],
+        [g[0], g[0], g[0], cv.neg(cv.mul(3, g[0]))],
+        [g[0], cv.neg(g[0]), g[1], cv.neg(g[1])],
+        close_sum([g[2]] * 9, cv),
+        close_sum([g[3]] * 2000, cv),
+        [None, None],
+        [],
+    ]
+    for pts in cases:
+        P = oracle.pack_points(pts, cv.p) if pts else np.zeros((0, 12), np.uint64)
+        pos, neg = ctx.compute_divisor_witness_naive(P)
+        rpos, rneg = oracle.divisor_witness_naive(cv.id, P)
+        assert pos.shape == rpos.shape and (pos == rpos).all(), len(pts)
+        assert neg.shape == rneg.shape and (neg == rneg).all(), len(pts)
+    with pytest.raises(eagen.EagenError) as ei:
+        ctx.compute_divisor_witness_naive(oracle.pack_points([g[0], g[1]], cv.p))
+    assert ei.value.status == eagen.E_SUM_NONZERO
