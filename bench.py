@@ -158,6 +158,8 @@ def main():
     ap.add_argument("--log-n", type=int, default=20, help="points per GPU = 2^log_n")
     ap.add_argument("--ref-log-n", type=int, default=11, help="points per CPU reference step")
     ap.add_argument("--cpu-log-n", type=int, default=11, help="points of the cpu_baseline sample")
+    ap.add_argument("--curve", default="pallas", choices=["pallas", "vesta", "grumpkin"],
+                    help="BASELINE config 4 is --curve vesta --log-n 21 under torchrun with 8 ranks (2^24 points)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -180,11 +182,11 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    ctx = eg.Context("pallas", local)
+    ctx = eg.Context(args.curve, local)
     ctx.set_profiling(True)
     n_local = 1 << args.log_n
     n_total = n_local * world
-    d = eg.num_digits(eg.PALLAS, BASE)
+    d = eg.num_digits({"pallas": eg.PALLAS, "vesta": eg.VESTA, "grumpkin": eg.GRUMPKIN}[args.curve], BASE)
 
     # synthetic inputs generated on the device (resident in HBM before the timed region)
     d_s = torch.empty(n_local * 32, dtype=torch.uint8, device=dev)
@@ -310,8 +312,8 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (256-bit Montgomery integer arithmetic)", "data": "synthetic",
-        "config": {"workload": "Pallas MSM witness 2^%d points per GPU (%d total), base 5, d=%d, canonical (a,b) for all %d digit positions"
-                               % (args.log_n, n_total, d, d),
+        "config": {"workload": "%s MSM witness 2^%d points per GPU (%d total), base 5, d=%d, canonical (a,b) for all %d digit positions"
+                               % (args.curve.capitalize(), args.log_n, n_total, d, d),
                    "l2": "inputs (128 MiB/GPU) and the ~9 GB working set exceed the 126 MB L2; no explicit flush",
                    "parallelism": "single GPU" if world == 1 else "point range sharded x%d, digit-position trees sharded x%d" % (world, world)},
         "wall_ms_per_step": wall_ms / args.steps,

@@ -49,6 +49,7 @@ ABI_SYMBOLS = [
     "eagen_set_profiling", "eagen_profile_reset", "eagen_profile_json", "eagen_microbench",
     "eagen_dev_negbase", "eagen_dev_ntt", "eagen_lhs_witness_stream", "eagen_lhs_witness_stream_layout",
     "eagen_table_entry_by_id", "eagen_msm", "eagen_prepare_scalar_witness", "eagen_divisor_witness_naive",
+    "eagen_circuit_sizes", "eagen_result_copy_padded", "eagen_result_eval", "eagen_to_curve_x", "eagen_y_from_x", "eagen_slope",
 ]
 SELFTEST_SYMBOLS = ["eagen_selftest_field", "eagen_selftest_curve", "eagen_selftest_negbase_params", "eagen_selftest_negbase_digits",
                     "eagen_selftest_ntt_plan"]
@@ -126,6 +127,12 @@ def lib():
         L.eagen_dev_synth_inputs.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t, C.c_void_p, C.c_void_p]
         L.eagen_prepare_scalar_witness.argtypes = [C.c_void_p, U64P, C.c_size_t, C.c_uint8, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t]
         L.eagen_divisor_witness_naive.argtypes = [C.c_void_p, U64P, C.c_size_t, U64P, C.POINTER(C.c_size_t), U64P, C.POINTER(C.c_size_t)]
+        L.eagen_circuit_sizes.argtypes = [C.c_size_t, C.c_uint8, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.eagen_result_copy_padded.argtypes = [C.c_void_p, C.c_size_t, C.c_uint8, U64P, U64P]
+        L.eagen_result_eval.argtypes = [C.c_void_p, C.c_void_p, U64P, C.c_size_t, U64P]
+        L.eagen_to_curve_x.argtypes = [C.c_int, U64P, U64P]
+        L.eagen_y_from_x.argtypes = [C.c_int, U64P, U64P, C.POINTER(C.c_int)]
+        L.eagen_slope.argtypes = [C.c_int, U64P, U64P]
         L.eagen_selftest_field.argtypes = [C.c_int, C.c_int, U64P, U64P, U64P]
         L.eagen_selftest_curve.argtypes = [C.c_int, C.c_int, U64P, U64P, C.c_uint32, U64P]
         L.eagen_selftest_negbase_params.argtypes = [C.c_int, C.c_uint8, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -169,6 +176,40 @@ def table_entry_by_id(curve, base, idx):
     if rc:
         raise EagenError(rc, lib().eagen_status_string(rc).decode())
     return out
+
+
+def circuit_sizes(num_pts, base):
+    """(a_size, b_size) of the circuit's coefficient columns (reference: src/config.rs:641-642)"""
+    a, b = C.c_size_t(), C.c_size_t()
+    rc = lib().eagen_circuit_sizes(num_pts, C.c_uint8(base), C.byref(a), C.byref(b))
+    if rc:
+        raise EagenError(rc, lib().eagen_status_string(rc).decode())
+    return a.value, b.value
+
+
+def _challenge(fn, name, curve, arr, with_flag=False):
+    a = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1)
+    out = np.zeros(4, dtype=np.uint64)
+    flag = C.c_int(-1)
+    rc = fn(curve, _p64(a), _p64(out), C.byref(flag)) if with_flag else fn(curve, _p64(a), _p64(out))
+    if rc:
+        raise EagenError(rc, name + ": " + lib().eagen_last_error(None).decode())
+    return (out, flag.value) if with_flag else out
+
+
+def to_curve_x(curve, c):
+    """reference: src/config.rs:165-176 (EagenError E_DOMAIN where the reference's loop would never end)"""
+    return _challenge(lib().eagen_to_curve_x, "to_curve_x", curve, c)
+
+
+def y_from_x(curve, x):
+    """reference: src/config.rs:178-183 -> (y, is_square)"""
+    return _challenge(lib().eagen_y_from_x, "y_from_x", curve, x, True)
+
+
+def slope(curve, x, y):
+    """reference: src/config.rs:185-188"""
+    return _challenge(lib().eagen_slope, "slope", curve, np.concatenate([np.asarray(x, np.uint64).reshape(4), np.asarray(y, np.uint64).reshape(4)]))
 
 
 def omega_pow(curve, exp2):
@@ -234,6 +275,21 @@ class WitnessResult:
 
     def total_bytes(self):
         return lib().eagen_result_total_bytes(self._h)
+
+    def padded(self, num_pts, base):
+        """(a, b) as the circuit's fixed-size rows: (nf, a_size, 4) and (nf, b_size, 4), zero padded (src/config.rs:641-642)"""
+        a_size, b_size = circuit_sizes(num_pts, base)
+        a = np.zeros((self.num_functions, a_size, 4), dtype=np.uint64)
+        b = np.zeros((self.num_functions, b_size, 4), dtype=np.uint64)
+        self._ctx._chk(lib().eagen_result_copy_padded(self._h, num_pts, C.c_uint8(base), _p64(a), _p64(b)))
+        return a, b
+
+    def ev(self, pts):
+        """RegularFunction::ev of every function at the Jacobian points pts -> (nf, m, 4); coefficients stay on the device"""
+        p = _arr(pts, 12)
+        out = np.zeros((self.num_functions, len(p), 4), dtype=np.uint64)
+        self._ctx._chk(lib().eagen_result_eval(self._ctx._h, self._h, _p64(p), len(p), _p64(out)))
+        return out
 
     def copy_all_into(self, host_ptr, nbytes):
         w = C.c_size_t()

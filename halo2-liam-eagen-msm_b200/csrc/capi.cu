@@ -65,6 +65,87 @@ template <class FP> void table_entry(uint8_t base, size_t id, uint64_t* out) {
     }
     std::memcpy(out, acc.v, 32);
 }
+// ---- challenge-point helpers of the circuit (reference: src/config.rs:163-187), host side like the reference's ------------
+// a^e for a 256-bit exponent given as limbs
+template <class FP> Fe<FP> pow_limbs(const Fe<FP>& a, const uint32_t* e) {
+    Fe<FP> r = Fe<FP>::one();
+    for (int i = 7; i >= 0; --i)
+        for (int bit = 31; bit >= 0; --bit) {
+            r = sqr(r);
+            if ((e[i] >> bit) & 1) r = mul(r, a);
+        }
+    return r;
+}
+// Tonelli-Shanks with z = F::ROOT_OF_UNITY (order 2^S): the root x = a^((t+1)/2) * z^e that ff::helpers::sqrt_tonelli_shanks
+// computes (p - 1 = 2^S t).  Returns false for a non-residue.
+template <class FP> bool sqrt_ts(const Fe<FP>& a, Fe<FP>& root) {
+    if (a.is_zero()) { root = a; return true; }
+    uint32_t t[8], pm1[8];
+    for (int i = 0; i < 8; ++i) pm1[i] = FP::mod(i);
+    pm1[0] -= 1;   // p is odd
+    const unsigned S = FP::S, ws = S / 32, bs = S % 32;
+    for (int i = 0; i < 8; ++i) {
+        uint64_t lo = ((unsigned)i + ws < 8) ? pm1[i + ws] : 0, hi = ((unsigned)i + ws + 1 < 8) ? pm1[i + ws + 1] : 0;
+        t[i] = bs ? (uint32_t)((lo >> bs) | (hi << (32 - bs))) : (uint32_t)lo;
+    }
+    uint32_t e[8];   // (t - 1) / 2 = t >> 1 (t is odd)
+    for (int i = 0; i < 8; ++i) e[i] = (t[i] >> 1) | (i + 1 < 8 ? (t[i + 1] << 31) : 0);
+    Fe<FP> w = pow_limbs(a, e);
+    Fe<FP> x = mul(a, w), b = mul(x, w), z = Fe<FP>::root_of_unity();
+    unsigned v = S;
+    const Fe<FP> one = Fe<FP>::one();
+    while (!(b == one)) {
+        unsigned k = 0;
+        Fe<FP> b2 = b;
+        while (!(b2 == one)) { b2 = sqr(b2); ++k; if (k == v) return false; }
+        Fe<FP> zz = z;
+        for (unsigned i = 0; i + k + 1 < v; ++i) zz = sqr(zz);
+        x = mul(x, zz);
+        z = sqr(zz);
+        b = mul(b, z);
+        v = k;
+    }
+    root = x;
+    return true;
+}
+// x^3 + a x + b of the curve (a = 0 for all three curves)
+template <class CC> Fe<typename CC::Base> curve_rhs(const Fe<typename CC::Base>& x) { return add(mul(sqr(x), x), CC::b()); }
+// which: 0 to_curve_x, 1 y_from_x, 2 slope
+template <class CC> int challenge_op(int which, const uint64_t* in, uint64_t* out, int* flag) {
+    typedef Fe<typename CC::Base> F;
+    F x, y;
+    std::memcpy(x.v, in, 32);
+    if (which == 2) {
+        std::memcpy(y.v, in + 4, 32);
+        if (y.is_zero()) throw StatusError{EAGEN_E_DOMAIN, "slope: y = 0 (the reference's invert().unwrap() panics)"};
+        F three_x2 = mul(from_u32<typename CC::Base>(3), sqr(x));
+        F r = mul(three_x2, inv(dbl(y)));
+        std::memcpy(out, r.v, 32);
+        return 0;
+    }
+    F rhs = curve_rhs<CC>(x), root;
+    bool sq = sqrt_ts(rhs, root);
+    if (flag) *flag = sq ? 1 : 0;
+    if (which == 0) {
+        // the reference loops forever when c is not the x of a curve point (the loop never changes x, :170-173)
+        if (!sq) throw StatusError{EAGEN_E_DOMAIN, "to_curve_x: x^3 + b is not a square (the reference never returns here)"};
+        std::memcpy(out, x.v, 32);
+        return 0;
+    }
+    if (!sq) {   // sqrt_alt of a non-square: (false, sqrt(ROOT_OF_UNITY * value))
+        if (!sqrt_ts(mul(rhs, F::root_of_unity()), root)) throw StatusError{EAGEN_E_ARG, "sqrt_alt: internal error"};
+    }
+    std::memcpy(out, root.v, 32);
+    return 0;
+}
+int challenge_dispatch(int curve, int which, const uint64_t* in, uint64_t* out, int* flag) {
+    switch (curve) {
+        case EAGEN_CURVE_PALLAS: return challenge_op<Pallas>(which, in, out, flag);
+        case EAGEN_CURVE_VESTA: return challenge_op<Vesta>(which, in, out, flag);
+        case EAGEN_CURVE_GRUMPKIN: return challenge_op<Grumpkin>(which, in, out, flag);
+    }
+    throw StatusError{EAGEN_E_ARG, "unknown curve id"};
+}
 }  // namespace
 
 extern "C" {
@@ -294,6 +375,51 @@ int eagen_divisor_witness_naive(eagen_ctx* ctx, const uint64_t* pts, size_t n, u
         need(n == 0 || (pts && pos_lines && neg_lines), "eagen_divisor_witness_naive: null buffer");
         ctx->eng->naive_host(pts, n, pos_lines, n_pos, neg_lines, n_neg);
     });
+}
+
+// ---- circuit-facing layouts ---------------------------------------------------
+int eagen_circuit_sizes(size_t num_pts, uint8_t base, size_t* a_size, size_t* b_size) {
+    if (!a_size || !b_size || base < 2) return EAGEN_E_ARG;
+    *b_size = (num_pts + base + 1) / 2;   // src/config.rs:641
+    *a_size = (num_pts + base + 2) / 2;   // src/config.rs:642
+    return EAGEN_OK;
+}
+int eagen_result_copy_padded(eagen_result* r, size_t num_pts, uint8_t base, uint64_t* a_out, uint64_t* b_out) {
+    if (!r || base < 2) return EAGEN_E_ARG;
+    ResultImpl* x = r->r;
+    size_t a_size, b_size;
+    eagen_circuit_sizes(num_pts, base, &a_size, &b_size);
+    if (x->nf == 0) return EAGEN_OK;
+    if (!a_out || !b_out) return EAGEN_E_ARG;
+    for (size_t k = 0; k < x->nf; ++k)
+        if ((size_t)x->la[k] > a_size || (size_t)x->lb[k] > b_size) return EAGEN_E_LEN;
+    if (!x->A.p || !x->B.p) return EAGEN_E_ARG;
+    cudaSetDevice(x->device);
+    std::memset(a_out, 0, x->nf * a_size * 32);
+    std::memset(b_out, 0, x->nf * b_size * 32);
+    for (size_t k = 0; k < x->nf; ++k) {
+        size_t la = (size_t)x->la[k] * 32, lb = (size_t)x->lb[k] * 32;
+        if (la && cudaMemcpyAsync((char*)a_out + k * a_size * 32, (const char*)x->A.p + k * x->a_stride * 32, la, cudaMemcpyDeviceToHost, 0) != cudaSuccess) return EAGEN_E_CUDA;
+        if (lb && cudaMemcpyAsync((char*)b_out + k * b_size * 32, (const char*)x->B.p + k * x->b_stride * 32, lb, cudaMemcpyDeviceToHost, 0) != cudaSuccess) return EAGEN_E_CUDA;
+    }
+    return cudaStreamSynchronize(0) == cudaSuccess ? EAGEN_OK : EAGEN_E_CUDA;
+}
+int eagen_result_eval(eagen_ctx* ctx, eagen_result* r, const uint64_t* pts, size_t m, uint64_t* out) {
+    if (!ctx || !r) return EAGEN_E_ARG;
+    return guarded(ctx, [&] {
+        need(m == 0 || (pts && out), "eagen_result_eval: null buffer");
+        need(r->r->nf == 0 || (r->r->A.p && r->r->B.p), "eagen_result_eval: the result holds no device-resident functions");
+        ctx->eng->result_eval_host(r->r, pts, m, out);
+    });
+}
+int eagen_to_curve_x(int curve, const uint64_t* c, uint64_t* x_out) {
+    return guarded(nullptr, [&] { need(c && x_out, "eagen_to_curve_x: null buffer"); challenge_dispatch(curve, 0, c, x_out, nullptr); });
+}
+int eagen_y_from_x(int curve, const uint64_t* x, uint64_t* y_out, int* is_square) {
+    return guarded(nullptr, [&] { need(x && y_out, "eagen_y_from_x: null buffer"); challenge_dispatch(curve, 1, x, y_out, is_square); });
+}
+int eagen_slope(int curve, const uint64_t* xy, uint64_t* slope_out) {
+    return guarded(nullptr, [&] { need(xy && slope_out, "eagen_slope: null buffer"); challenge_dispatch(curve, 2, xy, slope_out, nullptr); });
 }
 
 int eagen_poly_mul(eagen_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* b, size_t lb, uint64_t* out) {

@@ -145,6 +145,7 @@ struct IEngine {
     virtual double msm_host(const uint64_t* scalars, const uint64_t* pts, size_t n, uint64_t* out_affine) = 0;
     virtual void scalar_witness_host(const uint64_t* scalars, size_t n, uint8_t base, uint32_t num_digits, uint32_t logtable, int mode, void* out) = 0;
     virtual void naive_host(const uint64_t* pts, size_t n, uint64_t* pos, size_t* n_pos, uint64_t* neg, size_t* n_neg) = 0;
+    virtual void result_eval_host(ResultImpl* r, const uint64_t* pts, size_t m, uint64_t* out) = 0;
     virtual double microbench(int which) = 0;
     virtual void set_profiling(bool on) = 0;
     virtual std::string profile_json() = 0;
@@ -746,6 +747,55 @@ public:
         if (nl[1]) EAGEN_CUDA(cudaMemcpyAsync(neg, lines[1], nl[1] * sizeof(Line), cudaMemcpyDeviceToHost, st_));
         EAGEN_CUDA(cudaStreamSynchronize(st_));
         *n_pos = nl[0]; *n_neg = nl[1];
+    }
+
+    // RegularFunction::ev of every function held by a device-resident result at m Jacobian points (reference:
+    // src/regular_functions_utils.rs:228-237); out: nf x m elements, function-major.  The coefficients never leave the device.
+    void result_eval_host(ResultImpl* r, const uint64_t* pts, size_t m, uint64_t* out) override {
+        use();
+        if (r->device != dev_) throw StatusError{EAGEN_E_ARG, "eagen_result_eval: the result lives on another device"};
+        const size_t nf = r->nf;
+        if (m == 0 || nf == 0) return;
+        int lmax = 1;
+        for (size_t k = 0; k < nf; ++k) lmax = std::max(lmax, std::max(r->la[k], r->lb[k]));
+        const size_t len = (size_t)lmax;
+        const int nchunks = (int)((len + EVAL_CHUNK - 1) / EVAL_CHUNK);
+        std::vector<int> lens(2 * nf);
+        for (size_t k = 0; k < nf; ++k) { lens[k] = r->la[k]; lens[nf + k] = r->lb[k]; }
+        int* dl = (int*)cnt_.ensure(2 * nf * sizeof(int));
+        EAGEN_CUDA(cudaMemcpyAsync(dl, lens.data(), 2 * nf * sizeof(int), cudaMemcpyHostToDevice, st_));
+        const size_t batch = 64;
+        F* dp = (F*)in_points_.ensure(std::min(m, batch) * 96);
+        Aff* T = (Aff*)tpts_.ensure(std::min(m, batch) * sizeof(Aff));
+        F* zs = (F*)den_.ensure(std::min(m, batch) * 32);
+        F* X = (F*)wk_.ensure(std::min(m, batch) * len * 32);
+        F* part = (F*)binv_.ensure(std::min(m, batch) * nf * (size_t)nchunks * 64);
+        F* dout = (F*)oa_.ensure(nf * std::min(m, batch) * 32);
+        std::vector<uint64_t> tmp(nf * std::min(m, batch) * 4);
+        for (size_t j0 = 0; j0 < m; j0 += batch) {
+            const size_t mb = std::min(batch, m - j0);
+            EAGEN_CUDA(cudaMemcpyAsync(dp, pts + j0 * 12, mb * 96, cudaMemcpyHostToDevice, st_));
+            launch(k_jac_z<FB>, mb, 256, (const F*)dp, mb, zs);
+            batch_invert(zs, mb);
+            launch(k_jac_to_affine<FB>, mb, 256, (const F*)dp, (const F*)zs, mb, T);
+            {
+            Scope ps(this, "result_eval", (double)mb * (double)r_total_elems(r) * 32.0, (double)mb * ((double)r_total_elems(r) + (double)len));
+            launch(k_pow_init<FB>, mb, 64, (const Aff*)T, mb, len, X);
+            for (size_t half = 1; half + 1 < len; half *= 2)
+                launch2d(k_pow_step<FB>, dim3((unsigned)((half + 255) / 256), (unsigned)mb), 256, X, len, half, len);
+            launch2d(k_eval_chunks<FB>, dim3((unsigned)nchunks, (unsigned)nf, (unsigned)mb), EVAL_THREADS, (const F*)r->A.p, r->a_stride,
+                     (const F*)r->B.p, r->b_stride, (const int*)dl, (const int*)(dl + nf), (const F*)X, len, nchunks, part);
+            launch(k_eval_finish<FB>, nf * mb, 128, (const F*)part, nchunks, (int)nf, (const Aff*)T, mb, dout);
+            }
+            EAGEN_CUDA(cudaMemcpyAsync(tmp.data(), dout, nf * mb * 32, cudaMemcpyDeviceToHost, st_));
+            sync_check();
+            for (size_t k = 0; k < nf; ++k) std::memcpy(out + (k * m + j0) * 4, tmp.data() + k * mb * 4, mb * 32);
+        }
+    }
+    static size_t r_total_elems(const ResultImpl* r) {
+        size_t t = 0;
+        for (size_t k = 0; k < r->nf; ++k) t += (size_t)r->la[k] + (size_t)r->lb[k];
+        return t;
     }
 
 private:

@@ -1216,6 +1216,84 @@ __global__ void k_naive_finish(const Affine<FP>* __restrict__ list, const int2* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// RegularFunction::ev for every function of a device-resident result at m points (reference:
+// src/regular_functions_utils.rs:228-237; the circuit evaluates each f_k at the challenge point, src/config.rs:166-187).
+// Horner over 2^19 coefficients is serial, so the evaluation is a dot product with a table of powers of x:
+//   k_pow_step   X[j][2^s + i] = X[j][i] * X[j][2^s], 1 <= i <= 2^s   (log2(len) launches build x^0 .. x^(len-1) for all m points)
+//   k_eval_chunks   per (chunk of 2048 coefficients, function, point): partial sums of a_k . X_j and b_k . X_j
+//   k_eval_finish   out[k][j] = sum of a-partials + y_j * sum of b-partials
+// Field addition is exact, so the order of the partial sums does not change a bit of the result.
+// ------------------------------------------------------------------------------------------------
+template <class FP>
+__global__ void k_pow_init(const Affine<FP>* __restrict__ pts, size_t m, size_t stride, Fe<FP>* __restrict__ X) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    stg(X + j * stride, Fe<FP>::one());
+    if (stride > 1) stg(X + j * stride + 1, ldg_aff(pts + j).x);
+}
+template <class FP>
+__global__ void k_pow_step(Fe<FP>* __restrict__ X, size_t stride, size_t half /* 2^s: x^0 .. x^half are known */, size_t len) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x + 1;   // 1 .. half
+    Fe<FP>* row = X + (size_t)blockIdx.y * stride;
+    if (i > half || half + i >= len) return;
+    stg(row + half + i, mul(ldg(row + i), ldg(row + half)));
+}
+constexpr int EVAL_THREADS = 256;
+constexpr int EVAL_PER_THREAD = 8;
+constexpr int EVAL_CHUNK = EVAL_THREADS * EVAL_PER_THREAD;
+template <class FP>
+EAGEN_D Fe<FP> block_sum(Fe<FP> v, Fe<FP>* sm) {
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int h = EVAL_THREADS / 2; h > 0; h >>= 1) {
+        if ((int)threadIdx.x < h) sm[threadIdx.x] = add(sm[threadIdx.x], sm[threadIdx.x + h]);
+        __syncthreads();
+    }
+    Fe<FP> r = sm[0];
+    __syncthreads();
+    return r;
+}
+template <class FP>
+__global__ void __launch_bounds__(EVAL_THREADS)
+k_eval_chunks(const Fe<FP>* __restrict__ A, size_t a_stride, const Fe<FP>* __restrict__ B, size_t b_stride, const int* __restrict__ la,
+              const int* __restrict__ lb, const Fe<FP>* __restrict__ X, size_t x_stride, int nchunks,
+              Fe<FP>* __restrict__ part /* [point][function][chunk][2] */) {
+    __shared__ Fe<FP> sm[EVAL_THREADS];
+    const int c = blockIdx.x, k = blockIdx.y, j = blockIdx.z, nf = gridDim.y;
+    const Fe<FP>* xr = X + (size_t)j * x_stride;
+    const int na = la[k], nb = lb[k];
+    Fe<FP> sa = Fe<FP>::zero(), sb = Fe<FP>::zero();
+    if (c * EVAL_CHUNK < na || c * EVAL_CHUNK < nb) {
+#pragma unroll 2
+        for (int r = 0; r < EVAL_PER_THREAD; ++r) {
+            const int i = c * EVAL_CHUNK + r * EVAL_THREADS + (int)threadIdx.x;
+            if (i >= na && i >= nb) break;
+            const Fe<FP> xp = ldg(xr + i);
+            if (i < na) sa = add(sa, mul(ldg(A + (size_t)k * a_stride + i), xp));
+            if (i < nb) sb = add(sb, mul(ldg(B + (size_t)k * b_stride + i), xp));
+        }
+    }
+    sa = block_sum(sa, sm);
+    sb = block_sum(sb, sm);
+    if (threadIdx.x == 0) {
+        Fe<FP>* o = part + (((size_t)j * nf + k) * nchunks + c) * 2;
+        stg(o, sa); stg(o + 1, sb);
+    }
+}
+template <class FP>
+__global__ void k_eval_finish(const Fe<FP>* __restrict__ part, int nchunks, int nf, const Affine<FP>* __restrict__ pts, size_t m,
+                              Fe<FP>* __restrict__ out /* [function][point] */) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)nf * m) return;
+    const size_t k = g / m, j = g - k * m;
+    const Fe<FP>* p = part + ((j * nf + k) * (size_t)nchunks) * 2;
+    Fe<FP> sa = Fe<FP>::zero(), sb = Fe<FP>::zero();
+    for (int c = 0; c < nchunks; ++c) { sa = add(sa, ldg(p + 2 * c)); sb = add(sb, ldg(p + 2 * c + 1)); }
+    const Affine<FP> pt = ldg_aff(pts + j);
+    stg(out + g, pt.is_identity() ? Fe<FP>::zero() : add(sa, mul(sb, pt.y)));   // like k_eval_function: 0 at the identity
+}
+
+// ------------------------------------------------------------------------------------------------
 // Synthetic inputs for tests and bench.py: scalars uniform in [0, 2^127) from SplitMix64,
 // points P_j = (a + j*b) * G for seed-derived 64-bit a, b (distinct points, no structure a kernel could exploit),
 // emitted as Jacobian triples with non-trivial z.

@@ -35,4 +35,22 @@ extern "C" {
     pub fn eagen_poly_mul(ctx: *mut eagen_ctx, a: *const u64, la: usize, b: *const u64, lb: usize, out: *mut u64) -> c_int;
     pub fn eagen_ntt(ctx: *mut eagen_ctx, data: *mut u64, log_n: u32, inverse: c_int) -> c_int;
     pub fn eagen_fft_precomp(curve: c_int, which: c_int, exp: u64, out: *mut u64) -> c_int;
+    pub fn eagen_msm(ctx: *mut eagen_ctx, scalars: *const u64, pts: *const u64, n: usize, out_affine: *mut u64, device_ms: *mut f64) -> c_int;
+    pub fn eagen_table_entry_by_id(curve: c_int, base: u8, id: usize, out: *mut u64) -> c_int;
+    pub fn eagen_prepare_scalar_witness(ctx: *mut eagen_ctx, scalars: *const u64, n: usize, base: u8, num_digits: u32, logtable: u32,
+                                        mode: c_int, out: *mut PswEntry, out_bytes: usize) -> c_int;
+    pub fn eagen_divisor_witness_naive(ctx: *mut eagen_ctx, pts: *const u64, n: usize, pos_lines: *mut u64, n_pos: *mut usize,
+                                       neg_lines: *mut u64, n_neg: *mut usize) -> c_int;
+    pub fn eagen_circuit_sizes(num_pts: usize, base: u8, a_size: *mut usize, b_size: *mut usize) -> c_int;
+    pub fn eagen_result_copy_padded(r: *mut eagen_result, num_pts: usize, base: u8, a_out: *mut u64, b_out: *mut u64) -> c_int;
+    pub fn eagen_result_eval(ctx: *mut eagen_ctx, r: *mut eagen_result, pts: *const u64, m: usize, out: *mut u64) -> c_int;
+    pub fn eagen_to_curve_x(curve: c_int, c: *const u64, x_out: *mut u64) -> c_int;
+    pub fn eagen_y_from_x(curve: c_int, x: *const u64, y_out: *mut u64, is_square: *mut c_int) -> c_int;
+    pub fn eagen_slope(curve: c_int, xy: *const u64, slope_out: *mut u64) -> c_int;
 }
+
+/// one entry of eagen_prepare_scalar_witness (32 bytes, see include/eagen_msm.h)
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct PswEntry { pub lo: u64, pub hi: u64, pub mask: u32, pub kind: u32, pub zero: u64 }
+pub const EAGEN_PSW_FAITHFUL: c_int = 0;
+pub const EAGEN_PSW_INTENDED: c_int = 1;

@@ -115,3 +115,22 @@ pub fn compute_divisor_witness<C: GpuCurve>(pts: Vec<C>) -> RegularFunction<C> w
         f
     })
 }
+
+/// reference: :483-495
+pub struct Arrangement<C: GpuCurve> where C::Base: FftPrecomp { pub pos: Vec<RegularFunction<C>>, pub neg: Vec<RegularFunction<C>> }
+
+/// reference: :502-551 (lines of the numerator and of the denominator, in the reference's push order)
+pub fn compute_divisor_witness_naive<C: GpuCurve>(pts: Vec<C>) -> Arrangement<C> where C::Base: FftPrecomp + PrimeField {
+    let packed = pack_points(&pts);
+    let cap = pts.len().max(1);
+    let (mut pos, mut neg) = (vec![0u64; cap * 12], vec![0u64; cap * 12]);
+    let (mut np, mut nn) = (cap, cap);
+    with_ctx(C::CURVE_ID, |ctx| unsafe {
+        check(ctx, eagen_divisor_witness_naive(ctx, packed.as_ptr(), pts.len(), pos.as_mut_ptr(), &mut np, neg.as_mut_ptr(), &mut nn))
+    });
+    let lines = |v: &[u64], k: usize| (0..k).map(|i| {
+        let l = &v[12 * i..12 * i + 12];   // lx | ly | lz  ->  from_line(lx, ly, lz): a = [lz, lx], b = [ly]
+        RegularFunction::new(Polynomial::new(vec![felt_from_limbs(&l[8..12]), felt_from_limbs(&l[0..4])]), Polynomial::new(vec![felt_from_limbs(&l[4..8])]))
+    }).collect::<Vec<_>>();
+    Arrangement { pos: lines(&pos, np), neg: lines(&neg, nn) }
+}

@@ -157,6 +157,32 @@ int eagen_prepare_scalar_witness(eagen_ctx* ctx, const uint64_t* scalars, size_t
 int eagen_divisor_witness_naive(eagen_ctx* ctx, const uint64_t* pts, size_t n, uint64_t* pos_lines, size_t* n_pos,
                                 uint64_t* neg_lines, size_t* n_neg);
 
+/* ---- circuit-facing layouts ---------------------------------------------- */
+
+/* the fixed column sizes the circuit gives the coefficients of every f_k        src/config.rs:641-642
+ * b_size = (num_pts + base + 1) / 2, a_size = (num_pts + base + 2) / 2 */
+int eagen_circuit_sizes(size_t num_pts, uint8_t base, size_t* a_size, size_t* b_size);
+
+/* all functions of a result as fixed-size rows, zero padded: a_out = nf x a_size elements, b_out = nf x b_size elements
+ * (row k = digit position k).  EAGEN_E_LEN when a function does not fit its row (for an even list length the canonical a_k has
+ * a_size + 1 coefficients: its leading 1 is the monic normalisation the circuit's sizes leave implicit). */
+int eagen_result_copy_padded(eagen_result* r, size_t num_pts, uint8_t base, uint64_t* a_out, uint64_t* b_out);
+
+/* RegularFunction::ev of EVERY function of a device-resident result at m points (the circuit evaluates each f_k at the
+ * challenge point)                                            src/regular_functions_utils.rs:228-237
+ * pts: m Jacobian points; out: nf x m elements, function-major.  The coefficients stay on the device (power table of x,
+ * chunked dot products).  Like eagen_eval_function, the value at the identity is 0 (the reference panics there). */
+int eagen_result_eval(eagen_ctx* ctx, eagen_result* r, const uint64_t* pts, size_t m, uint64_t* out);
+
+/* challenge post-processors over the curve's BASE field (host side, no device needed)      src/config.rs:163-187
+ * eagen_to_curve_x: returns c when c^3 + b is a square; EAGEN_E_DOMAIN otherwise (the reference's loop never terminates there).
+ * eagen_y_from_x : sqrt_alt(x^3 + b): *is_square = 1 and y = the root, or 0 and y = sqrt(ROOT_OF_UNITY * (x^3 + b)).
+ *                  The root is the one Tonelli-Shanks yields from z = F::ROOT_OF_UNITY (ff::helpers::sqrt_tonelli_shanks).
+ * eagen_slope    : xy = x | y (64 bytes) -> (3 x^2 + a) / (2 y); EAGEN_E_DOMAIN when y = 0 (reference: unwrap() panic). */
+int eagen_to_curve_x(int curve, const uint64_t* c, uint64_t* x_out);
+int eagen_y_from_x(int curve, const uint64_t* x, uint64_t* y_out, int* is_square);
+int eagen_slope(int curve, const uint64_t* xy, uint64_t* slope_out);
+
 /* ---- helper API of regular_functions_utils ------------------------------------------------------------ */
 
 /* &Polynomial * &Polynomial                                   src/regular_functions_utils.rs:209-216

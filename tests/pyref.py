@@ -87,6 +87,40 @@ class Curve:
         return r
 
 
+# multiplicative generators ff's field impls derive ROOT_OF_UNITY = g^t from (p - 1 = 2^S t)
+FIELD_GENERATOR = {"pallas_fp": 5, "pallas_fq": 5, "bn256_fr": 7}
+
+
+def sqrt_ff(field, a):
+    """ff::helpers::sqrt_tonelli_shanks restated: the root a^((t+1)/2) * z^e with z = ROOT_OF_UNITY = g^t.
+    Returns (is_square, root); for a non-residue the root is sqrt(ROOT_OF_UNITY * a) like Field::sqrt_alt."""
+    p = FIELDS[field]
+    s, t = 0, p - 1
+    while t % 2 == 0:
+        s, t = s + 1, t // 2
+    root = pow(FIELD_GENERATOR[field], t, p)
+
+    def ts(v):
+        if v % p == 0:
+            return 0
+        w = pow(v, (t - 1) // 2, p)
+        x, b, z, m = v * w % p, v * w * w % p, root, s
+        while b != 1:
+            k, b2 = 0, b
+            while b2 != 1:
+                b2, k = b2 * b2 % p, k + 1
+                if k == m:
+                    return None
+            zz = pow(z, 1 << (m - k - 1), p)
+            x, z = x * zz % p, zz * zz % p
+            b, m = b * z % p, k
+        return x
+    r = ts(a % p)
+    if r is not None:
+        return True, r
+    return False, ts(a * root % p)
+
+
 def negbase_decompose(x, base):
     acc = []
     while x != 0:

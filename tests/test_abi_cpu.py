@@ -175,3 +175,35 @@ def test_table_entry_by_id_matches_oracle_and_known_answers(eagen, oracle):
     for cname, fid in (("pallas", 0), ("vesta", 1), ("grumpkin", 2)):
         for base, idx in ((5, 1023), (17, 77), (2, 32767), (255, 9)):
             assert (eagen.table_entry_by_id(eagen.CURVE_IDS[cname], base, idx) == oracle.table_entry_by_id(fid, base, idx)).all()
+
+
+def test_challenge_point_helpers(eagen, oracle):
+    """to_curve_x / y_from_x / slope (reference: src/config.rs:163-187): host-side helpers of the C ABI against Python ints"""
+    for cname in ("pallas", "vesta", "grumpkin"):
+        cv = pyref.Curve(cname)
+        p = cv.p
+        rng = pyref.SplitMix64(len(cname))
+        seen = set()
+        for _ in range(24):
+            x = rng.next_bits(4) % p
+            rhs = (x ** 3 + cv.b) % p
+            want_sq, want_y = pyref.sqrt_ff(cv.base_field, rhs)
+            X = oracle.pack_felts([x], p)[0]
+            y, is_sq = eagen.y_from_x(cv.id, X)
+            yv = oracle.unpack_felts(y, p)[0]
+            assert bool(is_sq) == want_sq and yv == want_y
+            seen.add(want_sq)
+            if want_sq:
+                assert yv * yv % p == rhs
+                assert (eagen.to_curve_x(cv.id, X) == X).all()
+                sl = oracle.unpack_felts(eagen.slope(cv.id, X, y), p)[0]
+                assert sl == 3 * x * x * pow(2 * yv, -1, p) % p
+            else:
+                with pytest.raises(eagen.EagenError) as ei:
+                    eagen.to_curve_x(cv.id, X)
+                assert ei.value.status == eagen.E_DOMAIN
+        assert seen == {True, False}
+        with pytest.raises(eagen.EagenError) as ei:
+            eagen.slope(cv.id, oracle.pack_felts([3], p)[0], oracle.pack_felts([0], p)[0])
+        assert ei.value.status == eagen.E_DOMAIN
+    assert eagen.circuit_sizes(1000, 5) == (503, 503) and eagen.circuit_sizes(2, 2) == (3, 2)

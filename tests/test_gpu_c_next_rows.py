@@ -149,3 +149,42 @@ def test_divisor_witness_naive_degenerate(gpu_ctx, oracle, eagen):
     with pytest.raises(eagen.EagenError) as ei:
         ctx.compute_divisor_witness_naive(oracle.pack_points([g[0], g[1]], cv.p))
     assert ei.value.status == eagen.E_SUM_NONZERO
+
+
+# ---- circuit-facing layouts: padded rows and evaluation of every f_k at challenge points ----------------------
+@pytest.mark.parametrize("cname", CURVES)
+def test_result_eval_and_padded_rows(gpu_ctx, oracle, eagen, cname):
+    """RegularFunction::ev of all d functions on the device (src/regular_functions_utils.rs:228-237) against the oracle's
+    Horner evaluation of the copied coefficients, and the zero-padded a_size / b_size rows of src/config.rs:641-642"""
+    cv, ctx = pyref.Curve(cname), gpu_ctx(cname)
+    for n, flags in ((5001, eagen.CANONICAL), (300, eagen.RAW_TREE), (1, eagen.CANONICAL)):
+        S, P = ctx.synth_inputs(4242 + n, n)
+        res = ctx.compute_lhs_witness(S, P, 5, flags)
+        rng = pyref.SplitMix64(n)
+        q = gen_points(cv, 3, 77 + n) + [None]
+        zs = [rng.next_bits(4) % cv.p or 1 for _ in q]
+        Q = np.concatenate([oracle.pack_points(q, cv.p, zs), P[:2]])        # random points, the identity, two input points
+        got = res.ev(Q)
+        assert got.shape == (res.num_functions, len(Q), 4)
+        fns = res.functions()
+        for k in (0, 1, res.d // 2, res.d - 1):
+            for j in range(len(Q)):
+                if j == 3:
+                    assert not got[k, j].any()       # identity -> 0 by convention
+                    continue
+                want = oracle.eval_function(cv.id, fns[k].a, fns[k].b, Q[j])
+                assert (got[k, j] == np.asarray(want, dtype=np.uint64).reshape(4)).all(), (n, k, j)
+        # padded rows: n odd -> every list has at most n + base + 1 points, so every function fits
+        if n % 2 == 1 and flags == eagen.CANONICAL:
+            a_size, b_size = eagen.circuit_sizes(n, 5)
+            A, B = res.padded(n, 5)
+            assert A.shape == (res.d, a_size, 4) and B.shape == (res.d, b_size, 4)
+            for k in range(res.d):
+                la, lb = len(fns[k].a), len(fns[k].b)
+                assert (A[k, :la] == fns[k].a).all() and not A[k, la:].any()
+                assert (B[k, :lb] == fns[k].b).all() and not B[k, lb:].any()
+        if n > 1:   # rows too short for these functions
+            with pytest.raises(eagen.EagenError) as ei:
+                res.padded(0, 2)
+            assert ei.value.status == eagen.E_LEN
+        res.free()
