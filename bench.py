@@ -95,12 +95,12 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def oracle_sample_step(oracle_lib, eg_inputs, log_n):
+def oracle_sample_step(oracle_lib, eg_inputs, log_n, curve_id=0):
     """one bounded CPU step: the oracle's full compute_lhs_witness on 2^log_n points of the same generator"""
     S, P = eg_inputs
     n = 1 << log_n
     t0 = time.perf_counter()
-    oracle_lib.lhs_witness(0, S[:n], P[:n], BASE)
+    oracle_lib.lhs_witness(curve_id, S[:n], P[:n], BASE)
     return time.perf_counter() - t0
 
 
@@ -303,7 +303,7 @@ def main():
         cores = os.cpu_count() or 1
         oracle_lib.set_threads(cores)
         S, P = ctx.synth_inputs(0xEA6E0002, 1 << args.cpu_log_n)
-        sec = oracle_sample_step(oracle_lib, (S, P), args.cpu_log_n)
+        sec = oracle_sample_step(oracle_lib, (S, P), args.cpu_log_n, eg.CURVE_IDS[args.curve])
         cpu = {"value": (1 << args.cpu_log_n) / sec, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "oracle (C++ restatement of the reference algorithm; the Rust crate cannot be built here) on the first 2^%d points of the same "
                          "workload, all 56 divisor witnesses, %.1f s; per-point CPU cost grows ~log^2 n so this over-states CPU throughput at 2^20"

@@ -10,6 +10,9 @@
 //   eagen::negbase_utils::id_by_digit / digit_by_id        :46-56
 //   eagen::regular_functions_utils::{Polynomial, RegularFunction, compute_divisor_witness(_partial), FftPrecomp}
 //                                                          src/regular_functions_utils.rs:17-47,209-273,453-480
+//   eagen::negbase_utils::{Entry, prepare_scalar_witness}   src/negbase_utils.rs:39-43,79-124 (batched over scalars)
+//   eagen::regular_functions_utils::{Arrangement, compute_divisor_witness_naive}   src/regular_functions_utils.rs:483-551
+//   eagen::config::{to_curve_x, y_from_x, slope, circuit_sizes}   src/config.rs:163-187,641-642
 //
 // Where the reference panics, these functions throw eagen::Error carrying the ABI status.
 #pragma once
@@ -116,9 +119,72 @@ inline RegularFunction compute_divisor_witness(const Context& ctx, const std::ve
     return f;
 }
 
+// reference: struct Arrangement { pos, neg }, :483-495; a line is RegularFunction::from_line(lx, ly, lz): a = [lz, lx], b = [ly]
+struct Arrangement { std::vector<RegularFunction> pos, neg; };
+
+// reference: compute_divisor_witness_naive, :502-551
+inline Arrangement compute_divisor_witness_naive(const Context& ctx, const std::vector<JacobianPoint>& pts) {
+    size_t cap = pts.empty() ? 1 : pts.size(), np = cap, nn = cap;
+    std::vector<uint64_t> pos(cap * 12), neg(cap * 12);
+    ctx.check(eagen_divisor_witness_naive(ctx.raw(), pts.empty() ? nullptr : pts[0].data(), pts.size(), pos.data(), &np, neg.data(), &nn));
+    auto lines = [](const std::vector<uint64_t>& v, size_t k) {
+        std::vector<RegularFunction> out(k);
+        for (size_t i = 0; i < k; ++i) {
+            Felt lx, ly, lz;
+            for (int w = 0; w < 4; ++w) { lx[w] = v[12 * i + w]; ly[w] = v[12 * i + 4 + w]; lz[w] = v[12 * i + 8 + w]; }
+            out[i].a.poly = {lz, lx};
+            out[i].b.poly = {ly};
+        }
+        return out;
+    };
+    return Arrangement{lines(pos, np), lines(neg, nn)};
+}
+
 }  // namespace regular_functions_utils
 
+namespace config {
+
+// reference: a_size / b_size in LiamMSMCircuit::synthesize, src/config.rs:641-642 -> {a_size, b_size}
+inline std::pair<size_t, size_t> circuit_sizes(size_t num_pts, uint8_t base) {
+    size_t a = 0, b = 0;
+    int rc = eagen_circuit_sizes(num_pts, base, &a, &b);
+    if (rc != EAGEN_OK) throw Error(rc, eagen_status_string(rc));
+    return {a, b};
+}
+// reference: to_curve_x, y_from_x, slope, src/config.rs:163-187 (Error EAGEN_E_DOMAIN where the reference hangs or panics)
+inline Felt to_curve_x(eagen_curve c, const Felt& ch) { Felt o; int rc = eagen_to_curve_x(c, ch.data(), o.data()); if (rc != EAGEN_OK) throw Error(rc, eagen_last_error(nullptr)); return o; }
+inline Felt y_from_x(eagen_curve c, const Felt& x) { Felt o; int rc = eagen_y_from_x(c, x.data(), o.data(), nullptr); if (rc != EAGEN_OK) throw Error(rc, eagen_last_error(nullptr)); return o; }
+inline Felt slope(eagen_curve c, const Felt& x, const Felt& y) {
+    uint64_t xy[8]; Felt o;
+    for (int w = 0; w < 4; ++w) { xy[w] = x[w]; xy[4 + w] = y[w]; }
+    int rc = eagen_slope(c, xy, o.data());
+    if (rc != EAGEN_OK) throw Error(rc, eagen_last_error(nullptr));
+    return o;
+}
+
+}  // namespace config
+
 namespace negbase_utils {
+
+// reference: enum Entry { Scalar(BigInt), Bucket(i128), Limb(i128, u32) }, src/negbase_utils.rs:39-43 (one 32-byte ABI entry)
+struct Entry {
+    enum Kind : uint32_t { Scalar = 0, Bucket = 1, Limb = 2 };
+    uint64_t lo, hi;   // two's complement i128 (Scalar: the canonical scalar)
+    uint32_t mask, kind;
+    uint64_t zero;
+};
+static_assert(sizeof(Entry) == 32, "ABI entry is 32 bytes");
+
+// reference: prepare_scalar_witness, :79-124, for n scalars: out[(j * base + row) * (num_limbs + 1) + slot]
+inline std::vector<Entry> prepare_scalar_witness(const Context& ctx, const std::vector<Felt>& scalars, uint8_t base, uint32_t num_digits,
+                                                 uint32_t logtable, eagen_psw_mode mode = EAGEN_PSW_FAITHFUL) {
+    size_t num_limbs = ((size_t)num_digits + logtable - 1) / logtable;
+    std::vector<Entry> out(scalars.size() * (size_t)base * (num_limbs + 1));
+    ctx.check(eagen_prepare_scalar_witness(ctx.raw(), scalars.empty() ? nullptr : scalars[0].data(), scalars.size(), base, num_digits, logtable,
+                                           mode, out.data(), out.size() * sizeof(Entry)));
+    return out;
+}
+
 
 // reference: id_by_digit / digit_by_id, src/negbase_utils.rs:46-56
 inline std::optional<size_t> id_by_digit(uint8_t digit) { if (digit == 0) return std::nullopt; return (size_t)(digit - 1); }
