@@ -270,6 +270,7 @@ public:
 
     explicit Engine(int dev) : dev_(dev) {
         EAGEN_CUDA(cudaSetDevice(dev_));
+        EAGEN_CUDA(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev_));
         EAGEN_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
         EAGEN_CUDA(cudaStreamCreateWithFlags(&cst_, cudaStreamNonBlocking));
         EAGEN_CUDA(cudaMalloc(&d_err_, sizeof(int)));
@@ -847,6 +848,7 @@ private:
     }
 
     int dev_;
+    int sm_count_ = 148;
     std::shared_ptr<BufPool> pool_ = std::make_shared<BufPool>();
     cudaStream_t st_ = nullptr, cst_ = nullptr;  // compute stream, copy stream (streamed results)
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
@@ -979,7 +981,9 @@ private:
         if (n == 0) return;
         const size_t smem = ((size_t)prm.nw * NEGBASE_THREADS + prm.lut_n) * sizeof(uint32_t);
         const int vec = (n % 4 == 0) && (((uintptr_t)planes & 3) == 0);
-        k_negbase<FS><<<(unsigned)((n + NEGBASE_THREADS - 1) / NEGBASE_THREADS), NEGBASE_THREADS, smem, st_>>>(ds, n, prm, planes, rows, vec, d_err_);
+        const size_t chunks = (n + NEGBASE_THREADS - 1) / NEGBASE_THREADS;
+        const unsigned grid = (unsigned)std::min<size_t>(chunks, (size_t)sm_count_ * 12);   // persistent: a multiple of the SM count
+        k_negbase<FS><<<grid, NEGBASE_THREADS, smem, st_>>>(ds, n, prm, planes, rows, vec, d_err_);
         ++launches_;
         EAGEN_CUDA(cudaGetLastError());
     }

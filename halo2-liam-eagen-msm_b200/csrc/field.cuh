@@ -113,7 +113,7 @@ EAGEN_HD void reduce_once(uint32_t* a, uint32_t top) {
 }
 
 template <class FP>
-EAGEN_HD Fe<FP> add(const Fe<FP>& a, const Fe<FP>& b) {
+EAGEN_HD Fe<FP> add_portable(const Fe<FP>& a, const Fe<FP>& b) {
     Fe<FP> r;
     uint64_t c = 0;
 #pragma unroll
@@ -127,7 +127,7 @@ EAGEN_HD Fe<FP> add(const Fe<FP>& a, const Fe<FP>& b) {
 }
 
 template <class FP>
-EAGEN_HD Fe<FP> sub(const Fe<FP>& a, const Fe<FP>& b) {
+EAGEN_HD Fe<FP> sub_portable(const Fe<FP>& a, const Fe<FP>& b) {
     Fe<FP> r;
     uint64_t br = 0;
 #pragma unroll
@@ -147,10 +147,6 @@ EAGEN_HD Fe<FP> sub(const Fe<FP>& a, const Fe<FP>& b) {
     return r;
 }
 
-template <class FP>
-EAGEN_HD Fe<FP> neg(const Fe<FP>& a) { return sub(Fe<FP>::zero(), a); }
-template <class FP>
-EAGEN_HD Fe<FP> dbl(const Fe<FP>& a) { return add(a, a); }
 
 // Portable Montgomery product, CIOS over 32-bit limbs with 64-bit temporaries (host path; reference for the PTX path).
 template <class FP>
@@ -237,6 +233,67 @@ inline uint32_t opaque(uint32_t c) { return c; }
 #endif
 }  // namespace cc
 
+// final a < 2p -> [0, p) with a borrow chain and selects
+template <class FP>
+EAGEN_HD void reduce_once_cc(uint32_t* r) {
+    uint32_t s[8], brw;
+    cc::sub_cc(s[0], r[0], FP::mod(0));
+#pragma unroll
+    for (int i = 1; i < 8; ++i) cc::subc_cc(s[i], r[i], FP::mod(i));
+    cc::subc(brw, 0, 0);  // 0 - 0 - borrow: all ones when r < p
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = brw ? r[i] : s[i];
+}
+
+// Field addition / subtraction on carry chains (device) -- the 64-bit C form above compiles to ~40 / ~45 instructions per
+// operation (borrow extraction, sign shifts), the chains to 25 / 22: add.cc x8, trial subtraction sub.cc x8, one borrow, 8 selects.
+// Every modulus here is below 2^255, so a + b never carries out of limb 7.
+template <class FP>
+EAGEN_HD Fe<FP> add_chain(const Fe<FP>& a, const Fe<FP>& b) {
+    static_assert((FP::mod(7) >> 31) == 0, "add_chain assumes p < 2^255");
+    Fe<FP> r;
+    cc::add_cc(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) cc::addc_cc(r.v[i], a.v[i], b.v[i]);
+    cc::addc(r.v[7], a.v[7], b.v[7]);
+    reduce_once_cc<FP>(r.v);
+    return r;
+}
+template <class FP>
+EAGEN_HD Fe<FP> sub_chain(const Fe<FP>& a, const Fe<FP>& b) {
+    Fe<FP> r;
+    uint32_t mask;
+    cc::sub_cc(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) cc::subc_cc(r.v[i], a.v[i], b.v[i]);
+    cc::subc(mask, 0, 0);   // all ones when a < b
+    cc::add_cc(r.v[0], r.v[0], FP::mod(0) & mask);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) cc::addc_cc(r.v[i], r.v[i], FP::mod(i) & mask);
+    cc::addc(r.v[7], r.v[7], FP::mod(7) & mask);
+    return r;
+}
+template <class FP>
+EAGEN_HD Fe<FP> add(const Fe<FP>& a, const Fe<FP>& b) {
+#if defined(__CUDA_ARCH__)
+    return add_chain(a, b);
+#else
+    return add_portable(a, b);
+#endif
+}
+template <class FP>
+EAGEN_HD Fe<FP> sub(const Fe<FP>& a, const Fe<FP>& b) {
+#if defined(__CUDA_ARCH__)
+    return sub_chain(a, b);
+#else
+    return sub_portable(a, b);
+#endif
+}
+template <class FP>
+EAGEN_HD Fe<FP> neg(const Fe<FP>& a) { return sub(Fe<FP>::zero(), a); }
+template <class FP>
+EAGEN_HD Fe<FP> dbl(const Fe<FP>& a) { return add(a, a); }
+
 // (lo, hi) += c * m inside a carry chain, c a modulus limb (a compile-time constant once the caller's loop is unrolled).
 // Measured on B200 (tools/probe/pipe_probe.cu): IMAD.WIDE / IMAD.HI issue at 32 lanes/clk/SM, 32-bit IMAD at 64, IADD3 with
 // carry at 128 -- so limbs equal to 1 or a power of two are done with adds and shifts on the ALU pipe, zero limbs only
@@ -307,18 +364,6 @@ EAGEN_HD void mont_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi)
 #pragma unroll
     for (int j = 0; j < 8; j += 2) mad_const_pair(O[j], O[j + 1], FP::mod(j), m, j == 0, false);
     cc::addc(E[7], E[7], 0);
-}
-
-// final a < 2p -> [0, p) with a borrow chain and selects
-template <class FP>
-EAGEN_HD void reduce_once_cc(uint32_t* r) {
-    uint32_t s[8], brw;
-    cc::sub_cc(s[0], r[0], FP::mod(0));
-#pragma unroll
-    for (int i = 1; i < 8; ++i) cc::subc_cc(s[i], r[i], FP::mod(i));
-    cc::subc(brw, 0, 0);  // 0 - 0 - borrow: all ones when r < p
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = brw ? r[i] : s[i];
 }
 
 // Montgomery product on carry chains (device fast path; host-emulated for tests)

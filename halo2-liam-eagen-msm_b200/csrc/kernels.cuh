@@ -236,7 +236,10 @@ k_negbase(const Fe<FS>* __restrict__ scalars, size_t n, NegbaseParams prm, uint8
     uint32_t* lut = nb_sm + prm.nw * NEGBASE_THREADS;      // lut_n entries
     for (uint32_t v = threadIdx.x; v < prm.lut_n; v += NEGBASE_THREADS) lut[v] = negbase_lut_entry(v, prm.base, prm.g);
     __syncthreads();
-    const size_t j0 = (size_t)blockIdx.x * NEGBASE_THREADS;
+    // persistent blocks: the table (b^g entries, built with real divisions) is paid once per block, not once per 128 scalars
+    const size_t nchunks = (n + NEGBASE_THREADS - 1) / NEGBASE_THREADS;
+    for (size_t chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const size_t j0 = chunk * NEGBASE_THREADS;
     const size_t j = j0 + threadIdx.x;
     if (j < n) {
         Fe<FS> xm = ldg(scalars + j);
@@ -286,6 +289,8 @@ k_negbase(const Fe<FS>* __restrict__ scalars, size_t n, NegbaseParams prm, uint8
                 if (pos >= 0) rows[j * d + pos] = (uint8_t)(word >> (8 * k));
             }
         }
+    }
+    __syncthreads();   // W is rewritten by the next chunk
     }
 }
 
@@ -712,6 +717,19 @@ EAGEN_D void ntt_sts(uint4* sm, uint32_t e, const Fe<FP>& r) {
 #ifndef EAGEN_NTT_MINBLOCKS
 #define EAGEN_NTT_MINBLOCKS 4
 #endif
+// EAGEN_NTT_DIAG_NOMUL (diagnostic builds only, results are wrong): butterflies add the twiddle instead of multiplying by it,
+// to measure what the pass costs without its products
+// EAGEN_NTT_DIAG_NOTW (diagnostic): every twiddle index is folded into the first 8 table entries (no gather traffic)
+#ifdef EAGEN_NTT_DIAG_NOTW
+#define NTT_TWI(x) ((size_t)7 & (size_t)(x))
+#else
+#define NTT_TWI(x) (x)
+#endif
+#ifdef EAGEN_NTT_DIAG_NOMUL
+#define NTT_MUL(a, b) add(a, b)
+#else
+#define NTT_MUL(a, b) mul(a, b)
+#endif
 template <class FP, bool INVERSE>
 __global__ void __launch_bounds__(NTT_THREADS, EAGEN_NTT_MINBLOCKS)
 k_ntt_pass(NttPass<FP> a) {
@@ -774,33 +792,33 @@ k_ntt_pass(NttPass<FP> a) {
             // Global stages 1 and 0: the twiddles are 1, 1 and w_4 for every thread (jl = 0), so three of the four products
             // vanish (uniform branch).  Over a whole tree 2/t of all butterflies of a 2^t-point transform have w = 1; this
             // round alone carries three quarters of them.  Multiplying by the Montgomery 1 would give the same bits.
-            const Fe<FP> W1b = ldg(a.tw + ((size_t)1 << (a.tw_t - 2)));   // w_4 (or its inverse)
+            const Fe<FP> W1b = ldg(a.tw + NTT_TWI((size_t)1 << (a.tw_t - 2)));   // w_4 (or its inverse)
             if (INVERSE) {
                 Fe<FP> y0 = add(x0, x1), y1 = sub(x0, x1), y2 = add(x2, x3), y3 = sub(x2, x3);
-                Fe<FP> u3 = mul(y3, W1b);
+                Fe<FP> u3 = NTT_MUL(y3, W1b);
                 ntt_sts(sm, i0, add(y0, y2)); ntt_sts(sm, i0 + 2 * d, sub(y0, y2));
                 ntt_sts(sm, i0 + d, add(y1, u3)); ntt_sts(sm, i0 + 3 * d, sub(y1, u3));
             } else {
                 Fe<FP> y0 = add(x0, x2), y2 = sub(x0, x2);
-                Fe<FP> y1 = add(x1, x3), y3 = mul(sub(x1, x3), W1b);
+                Fe<FP> y1 = add(x1, x3), y3 = NTT_MUL(sub(x1, x3), W1b);
                 ntt_sts(sm, i0, add(y0, y1)); ntt_sts(sm, i0 + d, sub(y0, y1));
                 ntt_sts(sm, i0 + 2 * d, add(y2, y3)); ntt_sts(sm, i0 + 3 * d, sub(y2, y3));
             }
         } else {
-            const Fe<FP> W0 = ldg(a.tw + (jl << (a.tw_t - 1 - sgl)));
-            const Fe<FP> W1a = ldg(a.tw + (jl << (a.tw_t - 1 - sgh)));
-            const Fe<FP> W1b = ldg(a.tw + ((jl + ((size_t)1 << sgl)) << (a.tw_t - 1 - sgh)));
+            const Fe<FP> W0 = ldg(a.tw + NTT_TWI(jl << (a.tw_t - 1 - sgl)));
+            const Fe<FP> W1a = ldg(a.tw + NTT_TWI(jl << (a.tw_t - 1 - sgh)));
+            const Fe<FP> W1b = ldg(a.tw + NTT_TWI((jl + ((size_t)1 << sgl)) << (a.tw_t - 1 - sgh)));
             if (INVERSE) {   // decimation in time: stage slo (distance d), then stage slo+1 (distance 2d)
-                Fe<FP> v1 = mul(x1, W0), v3 = mul(x3, W0);
+                Fe<FP> v1 = NTT_MUL(x1, W0), v3 = NTT_MUL(x3, W0);
                 Fe<FP> y0 = add(x0, v1), y1 = sub(x0, v1), y2 = add(x2, v3), y3 = sub(x2, v3);
-                Fe<FP> u2 = mul(y2, W1a), u3 = mul(y3, W1b);
+                Fe<FP> u2 = NTT_MUL(y2, W1a), u3 = NTT_MUL(y3, W1b);
                 ntt_sts(sm, i0, add(y0, u2)); ntt_sts(sm, i0 + 2 * d, sub(y0, u2));
                 ntt_sts(sm, i0 + d, add(y1, u3)); ntt_sts(sm, i0 + 3 * d, sub(y1, u3));
             } else {         // decimation in frequency: stage slo+1 (distance 2d), then stage slo (distance d)
-                Fe<FP> y0 = add(x0, x2), y2 = mul(sub(x0, x2), W1a);
-                Fe<FP> y1 = add(x1, x3), y3 = mul(sub(x1, x3), W1b);
-                ntt_sts(sm, i0, add(y0, y1)); ntt_sts(sm, i0 + d, mul(sub(y0, y1), W0));
-                ntt_sts(sm, i0 + 2 * d, add(y2, y3)); ntt_sts(sm, i0 + 3 * d, mul(sub(y2, y3), W0));
+                Fe<FP> y0 = add(x0, x2), y2 = NTT_MUL(sub(x0, x2), W1a);
+                Fe<FP> y1 = add(x1, x3), y3 = NTT_MUL(sub(x1, x3), W1b);
+                ntt_sts(sm, i0, add(y0, y1)); ntt_sts(sm, i0 + d, NTT_MUL(sub(y0, y1), W0));
+                ntt_sts(sm, i0 + 2 * d, add(y2, y3)); ntt_sts(sm, i0 + 3 * d, NTT_MUL(sub(y2, y3), W0));
             }
         }
         __syncthreads();
@@ -823,14 +841,14 @@ k_ntt_pass(NttPass<FP> a) {
                 ntt_sts(sm, i1, sub(u, v));
                 continue;
             }
-            Fe<FP> wj = ldg(a.tw + (j << (a.tw_t - 1 - sg)));
+            Fe<FP> wj = ldg(a.tw + NTT_TWI(j << (a.tw_t - 1 - sg)));
             if (INVERSE) {
-                v = mul(v, wj);
+                v = NTT_MUL(v, wj);
                 ntt_sts(sm, i0, add(u, v));
                 ntt_sts(sm, i1, sub(u, v));
             } else {
                 ntt_sts(sm, i0, add(u, v));
-                ntt_sts(sm, i1, mul(sub(u, v), wj));
+                ntt_sts(sm, i1, NTT_MUL(sub(u, v), wj));
             }
         }
         __syncthreads();
