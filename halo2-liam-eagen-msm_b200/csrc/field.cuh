@@ -302,15 +302,19 @@ EAGEN_HD void mad_const_pair(uint32_t& lo, uint32_t& hi, uint32_t c, uint32_t m,
     if (c == 0) {
         cc::ripple_cc(lo);
         if (last) cc::addc(hi, hi, 0); else cc::ripple_cc(hi);
+#ifndef EAGEN_MUL_NO_ONE_LIMB
     } else if (c == 1) {
         if (first) cc::add_cc(lo, lo, m); else cc::addc_cc(lo, lo, m);
         if (last) cc::addc(hi, hi, 0); else cc::addc_cc(hi, hi, 0);
-    } else if ((c & (c - 1)) == 0) {
+#endif
+#ifndef EAGEN_MUL_NO_POW2_LIMB
+    } else if ((c & (c - 1)) == 0 && c != 1) {
         int k = 0;
         while ((c >> k) != 1) ++k;
         uint32_t l = m << k, h = m >> (32 - k);
         if (first) cc::add_cc(lo, lo, l); else cc::addc_cc(lo, lo, l);
         if (last) cc::addc(hi, hi, h); else cc::addc_cc(hi, hi, h);
+#endif
     } else {
         uint32_t cr = cc::opaque(c);
         if (first) cc::mad_lo_cc(lo, cr, m, lo); else cc::madc_lo_cc(lo, cr, m, lo);
