@@ -1058,15 +1058,26 @@ private:
         size_t per_tree = tree_bytes(nmax);
         size_t budget = (size_t)((double)(free_b + pooled_bytes()) * 0.80);
         uint32_t group = (uint32_t)std::max<size_t>(1, std::min<size_t>(npos, budget / std::max<size_t>(per_tree, 1)));
+        uint32_t first_group = group;
         if (so) {  // streamed output: several groups so that only the last group's D2H is exposed
             const char* e = getenv("EAGEN_STREAM_GROUPS");
             uint32_t ng = e ? (uint32_t)std::max(1, atoi(e)) : 2u;  // measured best at 2^20 (tools/e2e_groups.py)
-            group = std::min<uint32_t>(group, (npos + ng - 1) / ng);
+            // with two groups the first one is the larger: its copy hides behind the second group's compute, and only the
+            // (smaller) second group's copy is exposed at the end
+            const char* f = getenv("EAGEN_STREAM_FIRST_PCT");
+            uint32_t pct = f ? (uint32_t)std::min(95, std::max(5, atoi(f))) : 70u;   // 70/30 measured best by a hair (tools/e2e_groups.py)
+            if (ng == 2 && pct != 50u) {
+                first_group = std::min<uint32_t>(group, std::max<uint32_t>(1, (npos * pct + 50) / 100));
+                group = std::min<uint32_t>(group, std::max<uint32_t>(1, npos - std::min(npos, first_group)));
+            } else {
+                group = std::min<uint32_t>(group, (npos + ng - 1) / ng);
+                first_group = group;
+            }
         }
         int* tree_of_pos = (int*)tree_of_pos_.ensure((size_t)d * sizeof(int));
         std::vector<Aff> roots(npos);
-        for (uint32_t g0 = pos_begin; g0 < pos_end; g0 += group) {
-            uint32_t g1 = std::min(pos_end, g0 + group), nt = g1 - g0;
+        for (uint32_t g0 = pos_begin, step = first_group; g0 < pos_end; g0 += step, step = group) {
+            uint32_t g1 = std::min(pos_end, g0 + step), nt = g1 - g0;
             std::vector<int> map(d, -1), cnts(nt);
             for (uint32_t p = g0; p < g1; ++p) { map[p] = (int)(p - g0); cnts[p - g0] = hn[p]; }
             EAGEN_CUDA(cudaMemcpyAsync(tree_of_pos, map.data(), (size_t)d * sizeof(int), cudaMemcpyHostToDevice, st_));

@@ -207,3 +207,22 @@ def test_challenge_point_helpers(eagen, oracle):
             eagen.slope(cv.id, oracle.pack_felts([3], p)[0], oracle.pack_felts([0], p)[0])
         assert ei.value.status == eagen.E_DOMAIN
     assert eagen.circuit_sizes(1000, 5) == (503, 503) and eagen.circuit_sizes(2, 2) == (3, 2)
+
+
+def test_pasta_fft_precomp_matches_published_root_of_unity(eagen, oracle):
+    """The reference only carries FftPrecomp tables for bn256::Fr; the Pasta tables are new.  Their seed must be the
+    PrimeField::ROOT_OF_UNITY pasta_curves publishes (= 5^((p-1)/2^32), the recipe of src/scripts.rs:44-70), and the table
+    entries its squaring chain, its inverse and powers of 1/2."""
+    published = {
+        "pallas": 0x2bce74deac30ebda362120830561f81aea322bf2b7bb7584bdad6fabd87ea32f,   # pasta_curves Fp::ROOT_OF_UNITY
+        "vesta": 0x2de6a9b8746d3f589e5c4dfd492ae26e9bb97ea3c106f049a70e2c1102b6d05f,    # pasta_curves Fq::ROOT_OF_UNITY
+    }
+    for cname, root in published.items():
+        cv = pyref.Curve(cname)
+        p = cv.p
+        assert root == pow(5, (p - 1) >> 32, p) and pow(root, 1 << 31, p) == p - 1
+        for k in (0, 1, 7, 31, 32, 63):
+            w = oracle.unpack_felts(eagen.omega_pow(cv.id, k), p)[0]
+            wi = oracle.unpack_felts(eagen.omega_pow_inv(cv.id, k), p)[0]
+            h = oracle.unpack_felts(eagen.half_pow(cv.id, k), p)[0]
+            assert w == pow(root, 1 << min(k, 40), p) and w * wi % p == 1 and h * pow(2, k, p) % p == 1

@@ -129,3 +129,19 @@ def test_error_paths(oracle):
     with pytest.raises(oracle.OracleError):  # base 2 needs more than d digits for the top of the range
         oracle.lhs_witness(2, oracle.pack_felts([pyref.isqrt(pyref.FIELDS["bn256_fq"]) + 1, 1], pyref.FIELDS["bn256_fq"]),
                            oracle.pack_points(gen(pyref.Curve("grumpkin"), 2, 1)[0], pyref.FIELDS["bn256_fr"]), 2)
+
+
+def test_curve_parameters_pair_base_and_scalar_fields():
+    """The published generators lie on y^2 = x^3 + b and have the scalar field's order: Pallas / Vesta (-1, 2) with b = 5
+    (pasta_curves), Grumpkin (1, sqrt(-16)) with b = -17 (halo2curves) -- pins which field is C::Base and which is C::Scalar."""
+    for cname in ("pallas", "vesta", "grumpkin"):
+        cv = pyref.Curve(cname)
+        if cname == "grumpkin":
+            y = cv.sqrt((1 - 17) % cv.p)
+            assert y is not None
+            G = (1, y)
+        else:
+            G = (cv.p - 1, 2)
+        assert cv.on_curve(G)
+        assert cv.mul(cv.q, G) is None and cv.mul(cv.q - 1, G) == cv.neg(G)
+        assert pyref.isqrt(cv.q) + 2 < 1 << 128   # the witness path's scalar range fits 128 bits (K1 relies on it)
