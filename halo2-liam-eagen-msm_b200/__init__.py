@@ -38,7 +38,7 @@ PSW_DTYPE = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("mask", "<u4"), ("kind", "<
 
 # every symbol include/eagen_msm.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
-    "eagen_ctx_create", "eagen_ctx_destroy", "eagen_last_error", "eagen_status_string", "eagen_launch_count",
+    "eagen_ctx_create", "eagen_ctx_destroy", "eagen_last_error", "eagen_status_string", "eagen_launch_count", "eagen_fallback_count",
     "eagen_num_digits", "eagen_negbase_decompose", "eagen_precompute_multiplicities", "eagen_lhs_witness",
     "eagen_divisor_witness", "eagen_result_num_digits", "eagen_result_num_functions", "eagen_result_poly_len",
     "eagen_result_poly_copy", "eagen_result_carry", "eagen_result_carries", "eagen_result_digits",
@@ -79,6 +79,8 @@ def lib():
         L.eagen_status_string.restype = C.c_char_p
         L.eagen_launch_count.restype = C.c_uint64
         L.eagen_launch_count.argtypes = [C.c_void_p]
+        L.eagen_fallback_count.restype = C.c_uint64
+        L.eagen_fallback_count.argtypes = [C.c_void_p]
         L.eagen_ctx_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.eagen_ctx_destroy.argtypes = [C.c_void_p]
         L.eagen_num_digits.argtypes = [C.c_int, C.c_uint8, C.POINTER(C.c_uint32)]
@@ -341,6 +343,10 @@ class Context:
 
     def launch_count(self):
         return lib().eagen_launch_count(self._h)
+
+    def fallback_count(self):
+        """groups of divisor trees rebuilt on an isomorphic curve after a domain collision (x of an output point on the domain)"""
+        return lib().eagen_fallback_count(self._h)
 
     def microbench(self, which):
         v = C.c_double()

@@ -196,6 +196,7 @@ void eagen_ctx_destroy(eagen_ctx* ctx) {
 
 const char* eagen_last_error(const eagen_ctx* ctx) { return ctx ? ctx->err.c_str() : g_global_err.c_str(); }
 uint64_t eagen_launch_count(const eagen_ctx* ctx) { return ctx ? ctx->eng->launches() : 0; }
+uint64_t eagen_fallback_count(const eagen_ctx* ctx) { return ctx ? ctx->eng->iso_fallbacks() : 0; }
 
 int eagen_microbench(eagen_ctx* ctx, int which, double* ops_per_second) {
     if (!ctx || !ops_per_second || which < 0 || which > 1) return EAGEN_E_ARG;

@@ -129,6 +129,7 @@ struct IEngine {
     virtual ResultImpl* lhs_stream_host(const uint64_t* scalars, const uint64_t* pts, size_t n, uint8_t base, uint32_t flags, void* out, size_t out_bytes) = 0;
     virtual int device() const = 0;
     virtual uint64_t launches() const = 0;
+    virtual uint64_t iso_fallbacks() const = 0;
     virtual void negbase_host(const uint64_t* scalars, size_t n, uint8_t base, uint8_t* digits) = 0;
     virtual void multiples_host(const uint64_t* pts, size_t n, uint8_t base, uint64_t* out) = 0;
     virtual ResultImpl* lhs_host(const uint64_t* scalars, const uint64_t* pts, size_t n, uint8_t base, uint32_t flags) = 0;
@@ -292,6 +293,7 @@ public:
     }
     int device() const override { return dev_; }
     uint64_t launches() const override { return launches_; }
+    uint64_t iso_fallbacks() const override { return iso_fallbacks_; }
 
     // ---- per-kernel-group profiling: CUDA events on the launching stream + exact work counts from launch parameters
     void set_profiling(bool on) override { prof_on_ = on; }
@@ -572,7 +574,7 @@ public:
         std::vector<int> cnt{(int)n};
         Aff root;
         std::vector<Aff> roots(1);
-        run_trees(T, n, cnt, flags, res.get(), 0, 1, roots.data());
+        run_trees_safe(T, n, cnt, flags, res.get(), 0, 1, roots.data());
         EAGEN_CUDA(cudaEventRecord(ev1_, st_));
         sync_check();
         root = roots[0];
@@ -855,6 +857,7 @@ private:
     int* d_err_ = nullptr;
     int* d_one_ = nullptr;
     uint64_t launches_ = 0;
+    uint64_t iso_fallbacks_ = 0;   // trees rebuilt on an isomorphic curve after a domain collision
     int tw_max_ = 0;
     DevBuf tw_fwd_, tw_inv_, xt_, gt_;
     DevBuf in_scalars_, in_points_, planes_, rows_, table_, sums_, partials_, carries_, carries_proj_;
@@ -1090,7 +1093,7 @@ private:
             }
             // result slot of position p is k = d-1-p; within this result handle slots are relative to the range:
             // slot = (pos_end-1-p), so slot 0 is the highest position of the range (= lowest k)
-            run_trees(T, nmax, cnts, flags, res, /*first slot*/ pos_end - g1, /*reverse*/ -1, roots.data() + (g0 - pos_begin));
+            run_trees_safe(T, nmax, cnts, flags, res, /*first slot*/ pos_end - g1, /*reverse*/ -1, roots.data() + (g0 - pos_begin));
             if (so) {  // run_trees has synchronised the compute stream: this group's functions are final, copy them on the copy stream
                 for (size_t slot = pos_end - g1; slot < (size_t)(pos_end - g0); ++slot) {
                     uint8_t* dst = so->out + slot * (so->a_stride + so->b_stride) * 32;
@@ -1116,9 +1119,45 @@ private:
         return n * 64 + 2 * lc * 64 + pad * 32 * (4 + 8 + 2 + 3) + lc * sizeof(MergeDesc<FB>) / 2 + 4096;
     }
 
+    static F iso_gshift(uint32_t u) {   // (u^6 - 1) b
+        const F uu = from_u32<FB>(u), u2 = sqr(uu), u6 = mul(sqr(u2), u2);
+        return mul(sub(u6, F::one()), CC::b());
+    }
+    // run_trees with the collision fallback: when an output point's x-coordinate hits the evaluation domain (k_den raises
+    // KERR_COLLISION) and the caller wants the canonical form, the lists are mapped to an isomorphic curve and the trees rebuilt.
+    // T is modified in place; roots come back on the original curve.
+    void run_trees_safe(Aff* T, size_t cap, const std::vector<int>& cnts, uint32_t flags, ResultImpl* res, size_t first_slot, int dir, Aff* roots) {
+        run_trees(T, cap, cnts, flags, res, first_slot, dir, roots, 0);
+        if (flags & EAGEN_RAW_TREE) return;   // the raw function is tied to the reference's own tree on the original curve
+        const int nt = (int)cnts.size();
+        uint32_t total_u = 1;
+        static const uint32_t steps[4] = {2, 3, 5, 7};
+        for (int attempt = 0; attempt < 4; ++attempt) {
+            int e = 0;
+            EAGEN_CUDA(cudaMemcpy(&e, d_err_, sizeof(int), cudaMemcpyDeviceToHost));
+            if (!(e & KERR_COLLISION)) break;
+            e &= ~KERR_COLLISION;
+            EAGEN_CUDA(cudaMemcpy(d_err_, &e, sizeof(int), cudaMemcpyHostToDevice));
+            const F s = from_u32<FB>(steps[attempt]), s2 = sqr(s), s3 = mul(s2, s);
+            total_u *= steps[attempt];
+            // row 0 of the level-count table the previous run_trees call uploaded is the list length of every tree
+            launch(k_iso_points<FB>, cap * (size_t)nt, 256, T, cap, (const int*)lvlcnt_.p, nt, s2, s3);
+            EAGEN_CUDA(cudaStreamSynchronize(st_));
+            ++iso_fallbacks_;
+            run_trees(T, cap, cnts, flags, res, first_slot, dir, roots, total_u);
+        }
+        if (total_u != 1) {   // roots back to the original curve: (x / u^2, y / u^3)
+            const F u = from_u32<FB>(total_u), iu = inv(u), iu2 = sqr(iu), iu3 = mul(iu2, iu);
+            for (int tr = 0; tr < nt; ++tr)
+                if (!roots[tr].is_identity()) { roots[tr].x = mul(roots[tr].x, iu2); roots[tr].y = mul(roots[tr].y, iu3); }
+        }
+    }
+
     // Divisor witnesses of `nt` point lists (T + tree*cap, counts cnts[tree]) -> res slots.
     // slot(tree) = first_slot + (dir > 0 ? tree : nt-1-tree).  roots[tree] receives the root output point.
-    void run_trees(const Aff* T, size_t cap, const std::vector<int>& cnts, uint32_t flags, ResultImpl* res, size_t first_slot, int dir, Aff* roots) {
+    // iso_u != 0: T already holds the points mapped to y^2 = x^3 + u^6 b (see run_trees_safe and k_iso_points)
+    void run_trees(const Aff* T, size_t cap, const std::vector<int>& cnts, uint32_t flags, ResultImpl* res, size_t first_slot, int dir, Aff* roots,
+                   uint32_t iso_u = 0) {
         const int nt = (int)cnts.size();
         size_t nmax = 0;
         for (int c : cnts) nmax = std::max<size_t>(nmax, (size_t)c);
@@ -1237,8 +1276,12 @@ private:
             batch_invert(den, wm << t);
             {
                 Scope ps(this, "merge_pointwise", pts * 288.0, pts * 11.0);
-                launch(k_pointwise<CC>, wm << t, 128, (const MergeDesc<FB>*)desc, wm, t, xtab(t), gtab(t), (const F*)EA[e], (const F*)EB[e],
-                       (const F*)den, merges, nodes, EA[e ^ 1], EB[e ^ 1], 2 * Tn);
+                if (iso_u)
+                    launch(k_pointwise<CC, true>, wm << t, 128, (const MergeDesc<FB>*)desc, wm, t, xtab(t), gtab(t), (const F*)EA[e], (const F*)EB[e],
+                           (const F*)den, merges, nodes, EA[e ^ 1], EB[e ^ 1], 2 * Tn, iso_gshift(iso_u));
+                else
+                    launch(k_pointwise<CC, false>, wm << t, 128, (const MergeDesc<FB>*)desc, wm, t, xtab(t), gtab(t), (const F*)EA[e], (const F*)EB[e],
+                           (const F*)den, merges, nodes, EA[e ^ 1], EB[e ^ 1], 2 * Tn, F::zero());
             }
             // back to coefficients (unscaled: stored = T * true), compact parent slots
             ntt(true, W, EA[e ^ 1], 2 * Tn, (int)Tn, A[cur ^ 1], Tn + 1, (int)Tn, t, wm, cnt_of(l + 1), (int)merges, (size_t)present[l + 1]);
@@ -1260,6 +1303,11 @@ private:
         if ((flags & EAGEN_RAW_TREE) && L > 0) {  // stored root = 2^L * true coefficients
             launch2d(k_scale_const<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, A[cur], ra, (int)ra, half_pow(L));
             launch2d(k_scale_const<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, B[cur], rb, (int)rb, half_pow(L));
+        }
+        if (iso_u) {  // back to the original curve: a_i = a'_i u^(2i), b_i = b'_i u^(2i+3) (any common factor disappears in the monic form)
+            const F u = from_u32<FB>(iso_u), u2 = sqr(u), u3 = mul(u2, u);
+            launch2d(k_iso_unscale<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, A[cur], ra, (int)ra, u2, F::one());
+            launch2d(k_iso_unscale<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, B[cur], rb, (int)rb, u2, u3);
         }
         launch2d(k_find_top<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, (const F*)A[cur], ra, (int)ra, tops);
         launch2d(k_find_top<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, (const F*)B[cur], rb, (int)rb, tops + nt);

@@ -944,14 +944,17 @@ __global__ void k_den(const MergeDesc<FP>* __restrict__ desc, size_t nmerges, in
 #ifndef EAGEN_PW_MINBLOCKS
 #define EAGEN_PW_MINBLOCKS 6
 #endif
-template <class CC>
+// ISO: the tree is being built on the isomorphic curve y^2 = x^3 + u^6 b (collision fallback, see Engine::run_trees_safe), whose
+// right-hand side is the tabulated x^3 + b plus the constant gshift = (u^6 - 1) b.
+template <class CC, bool ISO>
 __global__ void __launch_bounds__(128, EAGEN_PW_MINBLOCKS)
 k_pointwise(const MergeDesc<typename CC::Base>* __restrict__ desc, size_t nmerges, int t,
                             const Fe<typename CC::Base>* __restrict__ xt /* x at position p */,
                             const Fe<typename CC::Base>* __restrict__ gt /* x^3 + b at position p */,
                             const Fe<typename CC::Base>* __restrict__ EA, const Fe<typename CC::Base>* __restrict__ EB,
                             const Fe<typename CC::Base>* __restrict__ dinv, size_t merges_per_tree, size_t nodes_per_tree,
-                            Fe<typename CC::Base>* __restrict__ OA, Fe<typename CC::Base>* __restrict__ OB, size_t out_stride) {
+                            Fe<typename CC::Base>* __restrict__ OA, Fe<typename CC::Base>* __restrict__ OB, size_t out_stride,
+                            Fe<typename CC::Base> gshift) {
     typedef typename CC::Base F;
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (nmerges << t)) return;
@@ -970,6 +973,7 @@ k_pointwise(const MergeDesc<typename CC::Base>* __restrict__ desc, size_t nmerge
         Fe<F> a2 = ldg(EA + c2), b2 = ldg(EB + c2);
         Fe<F> x = ldg(xt + p);
         Fe<F> gx = ldg(gt + p);
+        if (ISO) gx = add(gx, gshift);
         // products of the form (u + y v)(u' + y v') = (u u' + v v' g) + y (u v' + v u') with three multiplications for the
         // cross term (Karatsuba): 4 instead of 5 field products each
         if (mode == MERGE_SHORTCUT) {
@@ -1231,6 +1235,40 @@ __global__ void k_naive_finish(const Affine<FP>* __restrict__ list, const int2* 
     const size_t o = np - 1 - t;
     stg_aff(next + o, c);
     stg(&lines[o].lx, l.lx); stg(&lines[o].ly, l.ly); stg(&lines[o].lz, l.lz);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Collision fallback (canonical form only).  The pointwise division of a merge is undefined when an output point's
+// x-coordinate lies on the power-of-two evaluation domain -- which happens for natural inputs: x = -1 (the Pasta generator)
+// and x = 1 (the Grumpkin generator) are on EVERY domain.  The divisor witness is unique up to a constant, and
+// (x, y) -> (u^2 x, u^3 y) is an isomorphism onto y^2 = x^3 + u^6 b, so the tree is rebuilt there (x-coordinates move off the
+// domain) and mapped back:  f(x, y) = f'(u^2 x, u^3 y), i.e. a_i = a'_i u^(2i), b_i = b'_i u^(2i+3); the canonical (monic) form of
+// f is the one the direct computation would have produced.
+// ------------------------------------------------------------------------------------------------
+template <class FP>
+__global__ void k_iso_points(Affine<FP>* __restrict__ T, size_t cap, const int* __restrict__ cnt, int nt, Fe<FP> u2, Fe<FP> u3) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= cap * (size_t)nt) return;
+    const int tree = (int)(g / cap);
+    if ((long long)(g - (size_t)tree * cap) >= cnt[tree]) return;
+    Affine<FP> p = ldg_aff(T + g);
+    if (p.is_identity()) return;
+    p.x = mul(p.x, u2); p.y = mul(p.y, u3);
+    stg_aff(T + g, p);
+}
+// c_i *= u2^i * extra for the `len` coefficients of each of the gridDim.y polynomials (stride elements apart)
+template <class FP>
+__global__ void k_iso_unscale(Fe<FP>* __restrict__ C, size_t stride, int len, Fe<FP> u2, Fe<FP> extra) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)len) return;
+    Fe<FP> s = extra;
+    Fe<FP> w = u2;
+    for (uint32_t e = (uint32_t)i; e; e >>= 1) {
+        if (e & 1) s = mul(s, w);
+        w = sqr(w);
+    }
+    Fe<FP>* c = C + (size_t)blockIdx.y * stride + i;
+    stg(c, mul(ldg(c), s));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@ extern "C" {
     pub fn eagen_ctx_create(curve: c_int, device: c_int, out: *mut *mut eagen_ctx) -> c_int;
     pub fn eagen_ctx_destroy(ctx: *mut eagen_ctx);
     pub fn eagen_last_error(ctx: *const eagen_ctx) -> *const c_char;
+    pub fn eagen_fallback_count(ctx: *const eagen_ctx) -> u64;
     pub fn eagen_num_digits(curve: c_int, base: u8, d: *mut u32) -> c_int;
     pub fn eagen_negbase_decompose(ctx: *mut eagen_ctx, scalars: *const u64, n: usize, base: u8, digits: *mut u8) -> c_int;
     pub fn eagen_precompute_multiplicities(ctx: *mut eagen_ctx, pts: *const u64, n: usize, base: u8, out: *mut u64) -> c_int;

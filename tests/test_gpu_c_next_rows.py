@@ -188,3 +188,52 @@ def test_result_eval_and_padded_rows(gpu_ctx, oracle, eagen, cname):
                 res.padded(0, 2)
             assert ei.value.status == eagen.E_LEN
         res.free()
+
+
+# ---- domain collisions: x of an intermediate output point on the evaluation domain ------------------------------------
+def generator(cv):
+    """published generators: Pallas / Vesta (-1, 2), Grumpkin (1, sqrt(-16)); x = -1 and x = 1 lie on EVERY power-of-two domain"""
+    if cv.name == "grumpkin":
+        return (1, cv.sqrt((1 - 17) % cv.p))
+    return (cv.p - 1, 2)
+
+
+@pytest.mark.parametrize("cname", CURVES)
+def test_domain_collision_falls_back_to_isomorphic_curve(gpu_ctx, oracle, eagen, cname):
+    """Natural inputs built from the curve generator make an output point's x hit the evaluation domain (pointwise division by
+    zero).  The canonical witness must still equal the oracle's (the tree is rebuilt on y^2 = x^3 + u^6 b and mapped back);
+    only EAGEN_RAW_TREE, which is tied to the reference's tree on the original curve, reports EAGEN_E_DOMAIN."""
+    cv, ctx = pyref.Curve(cname), gpu_ctx(cname)
+    G = generator(cv)
+    assert cv.on_curve(G)
+    before = ctx.fallback_count()
+    # (1) the smallest lhs witness that collides: one point, the generator, scalar 6 = (1, 4, 1) in base -5
+    for sc, pts in (([6], [G]), ([6, 11, 3, 124, 0, 77], [G] * 6), (list(range(1, 41)), [G] * 40),
+                    ([7 * j + 1 for j in range(60)], [cv.mul(j % 5 + 1, G) for j in range(60)])):
+        S, P = oracle.pack_felts(sc, cv.q), oracle.pack_points(pts, cv.p)
+        ro = oracle.lhs_witness(cv.id, S, P, 5)
+        rg = ctx.compute_lhs_witness(S, P, 5, eagen.CANONICAL)
+        assert (rg.carries == ro.carries).all() and (rg.carry == ro.carry).all()
+        for k in range(ro.d):
+            f = rg.function(k)
+            assert f.a.shape == ro.ca[k].shape and (f.a == ro.ca[k]).all(), (len(sc), k)
+            assert f.b.shape == ro.cb[k].shape and (f.b == ro.cb[k]).all(), (len(sc), k)
+        rg.free()
+    assert ctx.fallback_count() > before, "these inputs are expected to exercise the fallback"
+    # (2) stand-alone divisor witness whose two child outputs are +G and -G: the denominator (x - x_G)^2 vanishes on the domain
+    lst = [cv.mul(2, G), cv.neg(cv.mul(3, G)), G]
+    P = oracle.pack_points(lst, cv.p)
+    before = ctx.fallback_count()
+    f = ctx.compute_divisor_witness(P)
+    r = oracle.divisor_witness(cv.id, P)
+    assert f.a.shape == r.ca[0].shape and (f.a == r.ca[0]).all() and f.b.shape == r.cb[0].shape and (f.b == r.cb[0]).all()
+    assert ctx.fallback_count() == before + 1
+    with pytest.raises(eagen.EagenError) as ei:
+        ctx.compute_divisor_witness(P, eagen.RAW_TREE)
+    assert ei.value.status == eagen.E_DOMAIN
+    # (3) partial form: the output point comes back on the original curve
+    lst = [cv.mul(2, G), cv.neg(cv.mul(3, G)), G, cv.mul(5, G), cv.mul(9, G)]
+    P = oracle.pack_points(lst, cv.p)
+    f, out = ctx.compute_divisor_witness_partial(P)
+    r = oracle.divisor_witness(cv.id, P, partial=True)
+    assert (f.a == r.ca[0]).all() and (f.b == r.cb[0]).all() and (out == r.output).all()

@@ -22,7 +22,7 @@ for curve in ("pallas", "vesta", "grumpkin"):
     ctx.negbase_decompose(S[:300], 5)
     d = eg.num_digits(eg.CURVE_IDS[curve], 5)
     ctx.prepare_scalar_witness(S, 5, d, 8, eg.PSW_INTENDED)
-    ctx.prepare_scalar_witness(S[:7], 5, d, 56, eg.PSW_FAITHFUL)
+    ctx.prepare_scalar_witness(S[:7], 5, d, 1, eg.PSW_FAITHFUL)
     _, out = ctx.compute_divisor_witness_partial(P[:64])
     import numpy as np
     closing = np.zeros((1, 12), dtype=np.uint64)
