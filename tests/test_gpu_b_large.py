@@ -99,3 +99,45 @@ def test_config3_2pow20_properties(gpu_ctx, oracle, eagen):
         assert other.any(axis=1).all()
     f0 = res.function(d - 1)  # iteration 0: tmp = [-carry] = [O]  ->  the constant 1
     assert len(f0.a) == 1 and len(f0.b) == 0 and (f0.a[0] == one).all()
+
+
+def test_config3_2pow20_norm_identity(gpu_ctx, oracle, eagen):
+    """Full-size check of EVERY coefficient: for the monic divisor witness f = a + y b of the n points of tmp_i,
+    f(Q) f(-Q) = a(x)^2 - (x^3 + b) b(x)^2 = (-1)^n prod_i (x - x(P_i)) at any curve point Q = (x, y).  Both sides are
+    evaluated at random points: the left one on the device from the resident coefficients (eagen_result_eval), the right one with
+    Python integers over all ~0.84 M points of the list (Schwartz-Zippel: a wrong coefficient anywhere fails with probability
+    ~ 1 - 2^-230)."""
+    cv, ctx = pyref.Curve("pallas"), gpu_ctx("pallas")
+    p = cv.p
+    n, base = 1 << 20, 5
+    S, P = ctx.synth_inputs(0xEA6E0002, n)
+    res = ctx.compute_lhs_witness(S, P, base, eagen.CANONICAL | eagen.KEEP_DIGITS)
+    d, digits, carries = res.d, res.digits, res.carries
+    mult = ctx.precompute_multiplicities(P, base)
+    rng = pyref.SplitMix64(2020)
+    Q = pyref.random_point(rng, cv)
+    QJ = oracle.pack_points([Q, cv.neg(Q)], p)
+    vals = res.ev(QJ)                                   # (d, 2, 4): f_k(Q), f_k(-Q) for every digit position
+    rinv = pow(pyref.R, -1, p)
+    xq_m = Q[0] * pyref.R % p                           # x(Q) in Montgomery form: (xq_m - xm_i) = R (x(Q) - x_i)
+    for i in (2, 29, d - 1):
+        rows, _ = build_tmp(mult, digits, carries, i, base)
+        xs = rows[:, :4].astype(object)
+        xm = xs[:, 0] + (xs[:, 1] << 64) + (xs[:, 2] << 128) + (xs[:, 3] << 192)
+        extra = []
+        if i and carries[i - 1].any():
+            extra += [oracle.unpack_affine(carries[i - 1], p)[0][0]] * base      # b copies of -carry_{i-1}: same x as carry_{i-1}
+        if carries[i].any():
+            extra.append(oracle.unpack_affine(carries[i], p)[0][0])
+        npts = len(xm) + len(extra)
+        acc = 1
+        for v in xm:
+            acc = acc * (xq_m - v) % p
+        acc = acc * pow(rinv, len(xm), p) % p
+        for x in extra:
+            acc = acc * (Q[0] - x) % p
+        want = acc if npts % 2 == 0 else (-acc) % p
+        k = d - 1 - i
+        fq, fmq = oracle.unpack_felts(vals[k, 0], p)[0], oracle.unpack_felts(vals[k, 1], p)[0]
+        assert fq * fmq % p == want, i
+    res.free()
