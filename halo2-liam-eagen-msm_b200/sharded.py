@@ -47,10 +47,13 @@ class ShardedWitness:
         self.last_result_bytes = 0
 
     def step(self, d_scalars, d_points, keep=None):
-        """one whole-job pass; returns this rank's wall milliseconds (device idle on both sides)"""
+        """one whole-job pass; returns this rank's milliseconds between two CUDA events (device idle on both sides).  The
+        engine's calls are synchronous and the collectives run on torch's stream, so the events recorded on that stream before the
+        first and after the last call bracket all of the rank's device work."""
         dist, ctx = self.dist, self.ctx
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
         ctx.dev_shard_sums(d_scalars.data_ptr(), d_points.data_ptr(), self.n_local, self.base,
                            self.planes.data_ptr(), self.table.data_ptr(), self.sums.data_ptr())
         dist.all_gather_into_tensor(self.all_sums, self.sums)
@@ -61,8 +64,9 @@ class ShardedWitness:
         ctx.dev_carry_chain(self.all_sums.data_ptr(), self.world, self.base, self.carries.data_ptr())
         res = ctx.dev_trees(planes.data_ptr(), self.all_table.data_ptr(), self.carries.data_ptr(), self.n_local * self.world,
                             self.base, self.pos[0], self.pos[1], self.flags)
+        ev1.record()
         torch.cuda.synchronize()
-        ms = (time.perf_counter() - t0) * 1e3
+        ms = ev0.elapsed_time(ev1)
         self.last_result_bytes = res.total_bytes()
         if keep is not None:
             keep.append(res)
