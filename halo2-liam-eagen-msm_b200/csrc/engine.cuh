@@ -861,7 +861,7 @@ private:
     int tw_max_ = 0;
     DevBuf tw_fwd_, tw_inv_, xt_, gt_;
     DevBuf in_scalars_, in_points_, planes_, rows_, table_, sums_, partials_, carries_, carries_proj_;
-    DevBuf cnt_, tree_n_, tree_of_pos_, tpts_;
+    DevBuf cnt_, tree_n_, tree_of_pos_, tpts_, isodeg_;
     std::unique_ptr<Scope> prof_scope_;
     DevBuf ptlev_, lvlcnt_, a_[2], b_[2], ea_, eb_, oa_, ob_, wk_, top_, twist_, den_, binv_, desc_, tops_, lead_;
 
@@ -1124,11 +1124,11 @@ private:
         return mul(sub(u6, F::one()), CC::b());
     }
     // run_trees with the collision fallback: when an output point's x-coordinate hits the evaluation domain (k_den raises
-    // KERR_COLLISION) and the caller wants the canonical form, the lists are mapped to an isomorphic curve and the trees rebuilt.
+    // KERR_COLLISION) the lists are mapped to an isomorphic curve and the trees rebuilt; both the canonical and the raw form are
+    // recovered exactly.
     // T is modified in place; roots come back on the original curve.
     void run_trees_safe(Aff* T, size_t cap, const std::vector<int>& cnts, uint32_t flags, ResultImpl* res, size_t first_slot, int dir, Aff* roots) {
         run_trees(T, cap, cnts, flags, res, first_slot, dir, roots, 0);
-        if (flags & EAGEN_RAW_TREE) return;   // the raw function is tied to the reference's own tree on the original curve
         const int nt = (int)cnts.size();
         uint32_t total_u = 1;
         static const uint32_t steps[4] = {2, 3, 5, 7};
@@ -1217,6 +1217,12 @@ private:
         std::vector<double> present(L + 1, 0.0);
         for (int l = 0; l <= L; ++l) for (int tr = 0; tr < nt; ++tr) present[l] += lv[(size_t)(l + 1) * nt + tr];
 
+        // raw function on the isomorphic curve: per-tree homogeneity degree k (see k_iso_points), counted by the leaf / descriptor kernels
+        int* iso_deg = nullptr;
+        if (iso_u && (flags & EAGEN_RAW_TREE)) {
+            iso_deg = (int*)isodeg_.ensure((size_t)nt * sizeof(int));
+            EAGEN_CUDA(cudaMemsetAsync(iso_deg, 0, (size_t)nt * sizeof(int), st_));
+        }
         // level 0: outputs -(P+Q) and the line functions
         size_t w0 = (size_t)nt * node_max[0];
         {
@@ -1227,7 +1233,7 @@ private:
         {
             Scope ps(this, "pair_points", present[0] * (128.0 + 32.0 + 64.0 + 128.0 + 64.0 + 96.0), present[0] * (4.0 + 2.0));
             launch(k_pair_finish<FB>, w0, 256, T, cap, (const int*)dlv, node_max[0], nt, (const F*)den, 1, PT + pt_off[0]);
-            launch(k_leaf_lines<FB>, w0, 256, T, cap, (const int*)dlv, (const Aff*)(PT + pt_off[0]), node_max[0], nt, A[0], B[0]);
+            launch(k_leaf_lines<FB>, w0, 256, T, cap, (const int*)dlv, (const Aff*)(PT + pt_off[0]), node_max[0], nt, A[0], B[0], iso_deg);
         }
 
         int cur = 0, e = 0;
@@ -1252,7 +1258,7 @@ private:
             {
                 Scope ps(this, "pair_points", present[l + 1] * (128.0 + 32.0 + 64.0 + 192.0 + 272.0), present[l + 1] * (4.0 + 5.0));
                 launch(k_pair_finish<FB>, wm, 256, (const Aff*)Pc, nodes, cnt_of(l), merges, nt, (const F*)den, 0, Pp);
-                launch(k_merge_desc<FB>, wm, 128, (const Aff*)Pc, nodes, cnt_of(l), (const Aff*)Pp, merges, nt, F::one(), desc);
+                launch(k_merge_desc<FB>, wm, 128, (const Aff*)Pc, nodes, cnt_of(l), (const Aff*)Pp, merges, nt, F::one(), desc, iso_deg);
             }
             // Children in the evaluation domain.  Positions [0, m) of each child's 2m-point buffer already hold its values on the
             // m-point domain (written by the previous level's merge); only the odd coset w_T * w_m^k is transformed here:
@@ -1306,8 +1312,25 @@ private:
         }
         if (iso_u) {  // back to the original curve: a_i = a'_i u^(2i), b_i = b'_i u^(2i+3) (any common factor disappears in the monic form)
             const F u = from_u32<FB>(iso_u), u2 = sqr(u), u3 = mul(u2, u);
-            launch2d(k_iso_unscale<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, A[cur], ra, (int)ra, u2, F::one());
-            launch2d(k_iso_unscale<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, B[cur], rb, (int)rb, u2, u3);
+            const F* per_tree = nullptr;
+            if (iso_deg) {   // raw form: divide tree tr by u^k_tr
+                std::vector<int> hk(nt);
+                EAGEN_CUDA(cudaMemcpyAsync(hk.data(), iso_deg, (size_t)nt * sizeof(int), cudaMemcpyDeviceToHost, st_));
+                EAGEN_CUDA(cudaStreamSynchronize(st_));
+                const F iu = inv(u);
+                std::vector<F> fac(nt);
+                for (int tr = 0; tr < nt; ++tr) {
+                    F r = F::one(), w = iu;
+                    for (uint32_t e = (uint32_t)hk[tr]; e; e >>= 1) { if (e & 1) r = mul(r, w); w = sqr(w); }
+                    fac[tr] = r;
+                }
+                F* dfac = (F*)lead_.ensure((size_t)std::max(nt, 1) * 32);
+                EAGEN_CUDA(cudaMemcpyAsync(dfac, fac.data(), (size_t)nt * 32, cudaMemcpyHostToDevice, st_));
+                EAGEN_CUDA(cudaStreamSynchronize(st_));   // `fac` is a stack temporary
+                per_tree = dfac;
+            }
+            launch2d(k_iso_unscale<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, A[cur], ra, (int)ra, u2, F::one(), per_tree);
+            launch2d(k_iso_unscale<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, B[cur], rb, (int)rb, u2, u3, per_tree);
         }
         launch2d(k_find_top<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, (const F*)A[cur], ra, (int)ra, tops);
         launch2d(k_find_top<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, (const F*)B[cur], rb, (int)rb, tops + nt);

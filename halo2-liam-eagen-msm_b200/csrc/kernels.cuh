@@ -596,7 +596,8 @@ EAGEN_D void line_coeffs(const Affine<FP>& a, const Affine<FP>& b, const Affine<
 template <class FP>
 __global__ void k_leaf_lines(const Affine<FP>* __restrict__ T, size_t t_stride, const int* __restrict__ t_cnt,
                              const Affine<FP>* __restrict__ outp, size_t out_stride, int ntrees,
-                             Fe<FP>* __restrict__ A /* stride 2 */, Fe<FP>* __restrict__ B /* stride 1 */) {
+                             Fe<FP>* __restrict__ A /* stride 2 */, Fe<FP>* __restrict__ B /* stride 1 */,
+                             int* __restrict__ iso_deg /* optional: per tree, += 5 for every leaf that is a line */) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= out_stride * ntrees) return;
     int tree = (int)((uint32_t)g / (uint32_t)out_stride);   // indices < 2^32
@@ -612,6 +613,7 @@ __global__ void k_leaf_lines(const Affine<FP>* __restrict__ T, size_t t_stride, 
         if (p.is_identity()) { p = q; q = Affine<FP>::identity(); }  // from_pair(O, Q) = from_point(Q)
         if (q.is_identity()) q = aneg(p);                             // from_point(P) = line(P, -P)
         line_coeffs(p, q, ldg_aff(outp + g), lx, ly, lz);
+        if (iso_deg) atomicAdd(iso_deg + tree, 5);
     }
     stg(A + 2 * g, lz);
     stg(A + 2 * g + 1, lx);
@@ -632,7 +634,7 @@ struct MergeDesc {
 template <class FP>
 __global__ void k_merge_desc(const Affine<FP>* __restrict__ child, size_t child_stride, const int* __restrict__ child_cnt,
                              const Affine<FP>* __restrict__ parent, size_t parent_stride, int ntrees, Fe<FP> tinv,
-                             MergeDesc<FP>* __restrict__ desc) {
+                             MergeDesc<FP>* __restrict__ desc, int* __restrict__ iso_deg /* optional: per tree, += 1 per generic merge */) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= parent_stride * ntrees) return;
     int tree = (int)((uint32_t)g / (uint32_t)parent_stride);
@@ -648,6 +650,7 @@ __global__ void k_merge_desc(const Affine<FP>* __restrict__ child, size_t child_
         if (a.is_identity() || b.is_identity()) dsc.mode = MERGE_SHORTCUT;
         else {
             dsc.mode = MERGE_GENERIC;
+            if (iso_deg) atomicAdd(iso_deg + tree, 1);
             dsc.alpha = a.x; dsc.beta = b.x;
             line_coeffs(aneg(a), aneg(b), ldg_aff(parent + g), dsc.lx, dsc.ly, dsc.lz);
             dsc.slz = mul(dsc.lz, tinv); dsc.slx = mul(dsc.lx, tinv); dsc.sly = mul(dsc.ly, tinv);
@@ -1243,7 +1246,9 @@ __global__ void k_naive_finish(const Affine<FP>* __restrict__ list, const int2* 
 // and x = 1 (the Grumpkin generator) are on EVERY domain.  The divisor witness is unique up to a constant, and
 // (x, y) -> (u^2 x, u^3 y) is an isomorphism onto y^2 = x^3 + u^6 b, so the tree is rebuilt there (x-coordinates move off the
 // domain) and mapped back:  f(x, y) = f'(u^2 x, u^3 y), i.e. a_i = a'_i u^(2i), b_i = b'_i u^(2i+3); the canonical (monic) form of
-// f is the one the direct computation would have produced.
+// f is the one the direct computation would have produced.  The RAW function is recovered exactly as well: every line is
+// homogeneous of degree 5 in u and every generic merge divides by u^4 (x - alpha)(x - beta), so the tree built on the isomorphic
+// curve is u^k times the reference's raw function with k = 5 * (leaves that are lines) + (generic merges), counted per tree.
 // ------------------------------------------------------------------------------------------------
 template <class FP>
 __global__ void k_iso_points(Affine<FP>* __restrict__ T, size_t cap, const int* __restrict__ cnt, int nt, Fe<FP> u2, Fe<FP> u3) {
@@ -1256,12 +1261,12 @@ __global__ void k_iso_points(Affine<FP>* __restrict__ T, size_t cap, const int* 
     p.x = mul(p.x, u2); p.y = mul(p.y, u3);
     stg_aff(T + g, p);
 }
-// c_i *= u2^i * extra for the `len` coefficients of each of the gridDim.y polynomials (stride elements apart)
+// c_i *= u2^i * extra (* per_tree[tree]) for the `len` coefficients of each of the gridDim.y polynomials (stride elements apart)
 template <class FP>
-__global__ void k_iso_unscale(Fe<FP>* __restrict__ C, size_t stride, int len, Fe<FP> u2, Fe<FP> extra) {
+__global__ void k_iso_unscale(Fe<FP>* __restrict__ C, size_t stride, int len, Fe<FP> u2, Fe<FP> extra, const Fe<FP>* __restrict__ per_tree) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)len) return;
-    Fe<FP> s = extra;
+    Fe<FP> s = per_tree ? mul(extra, ldg(per_tree + blockIdx.y)) : extra;
     Fe<FP> w = u2;
     for (uint32_t e = (uint32_t)i; e; e >>= 1) {
         if (e & 1) s = mul(s, w);

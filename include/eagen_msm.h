@@ -45,8 +45,8 @@ enum eagen_status {
     EAGEN_E_CUDA = -6,          /* CUDA runtime error (see eagen_last_error)                                     */
     EAGEN_E_NCCL = -7,          /* reserved for the collective layer                                             */
     EAGEN_E_DIGITS = -8,        /* negbase expansion longer than d digits (the reference truncates silently, :99) */
-    EAGEN_E_DOMAIN = -9,        /* an intermediate point's x lies on the power-of-two evaluation domain (only with
-                                   EAGEN_RAW_TREE; the canonical form is recomputed on an isomorphic curve)         */
+    EAGEN_E_DOMAIN = -9,        /* an intermediate point's x lies on the power-of-two evaluation domain even after the
+                                   trees were rebuilt on four isomorphic curves (see eagen_fallback_count)          */
     EAGEN_E_NO_DEVICE = -10,    /* no CUDA device: there is deliberately no CPU fallback                         */
     EAGEN_E_EMPTY = -11         /* group_merge of an empty list            src/regular_functions_utils.rs:382    */
 };
@@ -72,7 +72,7 @@ const char* eagen_status_string(int status);
 /* number of kernels this context has launched so far (bench.py reports the per-step delta as gpu_launches) */
 uint64_t eagen_launch_count(const eagen_ctx* ctx);
 /* how many times this context rebuilt a group of divisor trees on an isomorphic curve because an output point's x-coordinate
- * lay on the evaluation domain (canonical form only; EAGEN_RAW_TREE reports EAGEN_E_DOMAIN instead) */
+ * lay on the evaluation domain; both the canonical and the raw form come back exactly as a direct computation would give them */
 uint64_t eagen_fallback_count(const eagen_ctx* ctx);
 
 /* per-kernel-group profiling (CUDA events on the launching stream + exact byte / modmul counts from the launch
