@@ -1061,26 +1061,39 @@ private:
         size_t per_tree = tree_bytes(nmax);
         size_t budget = (size_t)((double)(free_b + pooled_bytes()) * 0.80);
         uint32_t group = (uint32_t)std::max<size_t>(1, std::min<size_t>(npos, budget / std::max<size_t>(per_tree, 1)));
-        uint32_t first_group = group;
-        if (so) {  // streamed output: several groups so that only the last group's D2H is exposed
-            const char* e = getenv("EAGEN_STREAM_GROUPS");
-            uint32_t ng = e ? (uint32_t)std::max(1, atoi(e)) : 2u;  // measured best at 2^20 (tools/e2e_groups.py)
-            // with two groups the first one is the larger: its copy hides behind the second group's compute, and only the
-            // (smaller) second group's copy is exposed at the end
-            const char* f = getenv("EAGEN_STREAM_FIRST_PCT");
-            uint32_t pct = f ? (uint32_t)std::min(95, std::max(5, atoi(f))) : 70u;   // 70/30 measured best by a hair (tools/e2e_groups.py)
-            if (ng == 2 && pct != 50u) {
-                first_group = std::min<uint32_t>(group, std::max<uint32_t>(1, (npos * pct + 50) / 100));
-                group = std::min<uint32_t>(group, std::max<uint32_t>(1, npos - std::min(npos, first_group)));
-            } else {
-                group = std::min<uint32_t>(group, (npos + ng - 1) / ng);
-                first_group = group;
+        // group sizes: as large as the memory budget allows; for streamed output a decreasing schedule (per cent of the positions,
+        // EAGEN_STREAM_SPLIT, default 70,30) so that every group's copy hides behind the next group's compute and only the
+        // small last group's copy is exposed.  More, smaller groups shorten the exposed copy but add ~1300 launches each:
+        // 70,30 measured 3 ms faster than 60,30,10 on boxes with a fast host link (tools/e2e_groups.py)
+        std::vector<uint32_t> sizes;
+        if (so) {
+            std::vector<uint32_t> pct;
+            const char* e = getenv("EAGEN_STREAM_SPLIT");
+            std::string spec = e ? e : "70,30";
+            for (size_t i = 0; i < spec.size();) {
+                size_t j = spec.find(',', i);
+                if (j == std::string::npos) j = spec.size();
+                int v = atoi(spec.substr(i, j - i).c_str());
+                if (v > 0) pct.push_back((uint32_t)v);
+                i = j + 1;
             }
+            uint32_t left = npos;
+            for (size_t i = 0; i < pct.size() && left; ++i) {
+                uint32_t want = i + 1 == pct.size() ? left : std::min<uint32_t>(left, std::max<uint32_t>(1, (npos * pct[i] + 50) / 100));
+                while (want) {   // never more than the memory budget per group
+                    uint32_t g = std::min(want, group);
+                    sizes.push_back(g); want -= g; left -= g;
+                }
+            }
+            while (left) { uint32_t g = std::min(left, group); sizes.push_back(g); left -= g; }
+        } else {
+            for (uint32_t left = npos; left;) { uint32_t g = std::min(left, group); sizes.push_back(g); left -= g; }
         }
         int* tree_of_pos = (int*)tree_of_pos_.ensure((size_t)d * sizeof(int));
         std::vector<Aff> roots(npos);
-        for (uint32_t g0 = pos_begin, step = first_group; g0 < pos_end; g0 += step, step = group) {
-            uint32_t g1 = std::min(pos_end, g0 + step), nt = g1 - g0;
+        uint32_t g0 = pos_begin;
+        for (size_t gi = 0; gi < sizes.size(); g0 += sizes[gi], ++gi) {
+            uint32_t g1 = std::min(pos_end, g0 + sizes[gi]), nt = g1 - g0;
             std::vector<int> map(d, -1), cnts(nt);
             for (uint32_t p = g0; p < g1; ++p) { map[p] = (int)(p - g0); cnts[p - g0] = hn[p]; }
             EAGEN_CUDA(cudaMemcpyAsync(tree_of_pos, map.data(), (size_t)d * sizeof(int), cudaMemcpyHostToDevice, st_));
