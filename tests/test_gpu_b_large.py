@@ -101,20 +101,21 @@ def test_config3_2pow20_properties(gpu_ctx, oracle, eagen):
     assert len(f0.a) == 1 and len(f0.b) == 0 and (f0.a[0] == one).all()
 
 
-def test_config3_2pow20_norm_identity(gpu_ctx, oracle, eagen):
+@pytest.mark.parametrize("cname,log_n", [("pallas", 20), ("grumpkin", 18), ("vesta", 17)])
+def test_config3_norm_identity(gpu_ctx, oracle, eagen, cname, log_n):
     """Full-size check of EVERY coefficient: for the monic divisor witness f = a + y b of the n points of tmp_i,
     f(Q) f(-Q) = a(x)^2 - (x^3 + b) b(x)^2 = (-1)^n prod_i (x - x(P_i)) at any curve point Q = (x, y).  Both sides are
     evaluated at random points: the left one on the device from the resident coefficients (eagen_result_eval), the right one with
-    Python integers over all ~0.84 M points of the list (Schwartz-Zippel: a wrong coefficient anywhere fails with probability
+    Python integers over all points of the list (~0.84 M at 2^20; Grumpkin exercises the generic, non-sparse modulus at scale) (Schwartz-Zippel: a wrong coefficient anywhere fails with probability
     ~ 1 - 2^-230)."""
-    cv, ctx = pyref.Curve("pallas"), gpu_ctx("pallas")
+    cv, ctx = pyref.Curve(cname), gpu_ctx(cname)
     p = cv.p
-    n, base = 1 << 20, 5
+    n, base = 1 << log_n, 5
     S, P = ctx.synth_inputs(0xEA6E0002, n)
     res = ctx.compute_lhs_witness(S, P, base, eagen.CANONICAL | eagen.KEEP_DIGITS)
     d, digits, carries = res.d, res.digits, res.carries
     mult = ctx.precompute_multiplicities(P, base)
-    rng = pyref.SplitMix64(2020)
+    rng = pyref.SplitMix64(2020 + log_n)
     Q = pyref.random_point(rng, cv)
     QJ = oracle.pack_points([Q, cv.neg(Q)], p)
     vals = res.ev(QJ)                                   # (d, 2, 4): f_k(Q), f_k(-Q) for every digit position
