@@ -287,7 +287,10 @@ def main():
             traffic = None
     roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": traffic, "peak_source": peak_src, "launches": top["launches"], "avg_launch_ms": per_launch_ms,
-                "share_of_step": shares[top["kernel"]], "algorithmic_bytes_per_launch": top["bytes"] / max(top["launches"], 1)}
+                "share_of_step": shares[top["kernel"]], "algorithmic_bytes_per_launch": top["bytes"] / max(top["launches"], 1),
+                "note": "256-bit modular arithmetic: the kernel is bound by the heavy multiplier pipe (IMAD.WIDE), not by HBM -- ncu "
+                        "sm__pipe_fmaheavy_cycles_active 63-70 % in k_ntt_pass, 81 % in k_pointwise (profiles/r01_ntt_pointwise_full_raw.csv); "
+                        "see int_roofline for modmul/s against the measured pipe ceiling"}
     # integer-pipe view: Montgomery products per second over all profiled kernels against the measured ceilings
     imad_peak = ctx.microbench(0)
     modmul_peak = ctx.microbench(1)
