@@ -574,21 +574,19 @@ __global__ void k_pair_finish(const Affine<FP>* __restrict__ in, size_t in_strid
 }
 
 // line through affine a, b as (lx, ly, lz) = cross((ax,ay,1),(bx,by,1)); tangent fallback through c = -(a+b)
-// (reference: src/regular_functions_utils.rs:285-303 with z = 1; identity = (0,0,0))
+// (reference: src/regular_functions_utils.rs:285-303 with z = 1).  Precondition: neither a nor b is the identity -- every caller
+// substitutes from_point's partner -a (or skips the merge) before it gets here.
 template <class FP>
 EAGEN_D void line_coeffs(const Affine<FP>& a, const Affine<FP>& b, const Affine<FP>& c, Fe<FP>& lx, Fe<FP>& ly, Fe<FP>& lz) {
-    const bool ai = a.is_identity(), bi = b.is_identity();
-    Fe<FP> az = ai ? Fe<FP>::zero() : Fe<FP>::one(), bz = bi ? Fe<FP>::zero() : Fe<FP>::one();
-    lz = sub(mul(a.x, b.y), mul(a.y, b.x));
-    lx = ai ? (bi ? Fe<FP>::zero() : neg(b.y)) : (bi ? a.y : sub(a.y, b.y));   // ay*bz - az*by
-    ly = ai ? (bi ? Fe<FP>::zero() : Fe<FP>::zero()) : (bi ? Fe<FP>::zero() : sub(b.x, a.x));  // az*bx - ax*bz
-    if (ai && !bi) ly = Fe<FP>::zero();
-    (void)az; (void)bz;
+    lz = sub(mul(a.x, b.y), mul(a.y, b.x));   // ax*by - ay*bx
+    lx = sub(a.y, b.y);                       // ay*bz - az*by
+    ly = sub(b.x, a.x);                       // az*bx - ax*bz
     if (!lx.is_zero() || !ly.is_zero() || !lz.is_zero()) return;
+    // a == b: the cross product vanishes and the reference takes the line through a and c = -(a + b), the tangent (:296-302)
     const bool ci = c.is_identity();
     lz = sub(mul(a.x, c.y), mul(a.y, c.x));
-    lx = ai ? (ci ? Fe<FP>::zero() : neg(c.y)) : (ci ? a.y : sub(a.y, c.y));
-    ly = (ai || ci) ? Fe<FP>::zero() : sub(c.x, a.x);
+    lx = ci ? a.y : sub(a.y, c.y);
+    ly = ci ? Fe<FP>::zero() : sub(c.x, a.x);
 }
 
 // level-0 functions: a = [lz, lx], b = [ly]; both points identity -> the constant 1
