@@ -204,7 +204,7 @@ int eagen_microbench(eagen_ctx* ctx, int which, double* ops_per_second) {
 }
 int eagen_set_profiling(eagen_ctx* ctx, int on) {
     if (!ctx) return EAGEN_E_ARG;
-    ctx->eng->set_profiling(on != 0);
+    ctx->eng->set_profiling(on);
     return EAGEN_OK;
 }
 int eagen_profile_reset(eagen_ctx* ctx) {

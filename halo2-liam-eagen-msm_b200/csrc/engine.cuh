@@ -148,7 +148,7 @@ struct IEngine {
     virtual void naive_host(const uint64_t* pts, size_t n, uint64_t* pos, size_t* n_pos, uint64_t* neg, size_t* n_neg) = 0;
     virtual void result_eval_host(ResultImpl* r, const uint64_t* pts, size_t m, uint64_t* out) = 0;
     virtual double microbench(int which) = 0;
-    virtual void set_profiling(bool on) = 0;
+    virtual void set_profiling(int mode) = 0;
     virtual std::string profile_json() = 0;
     virtual void profile_reset() = 0;
     virtual void synth_dev(uint64_t seed, size_t n, void* d_scalars, void* d_pts) = 0;
@@ -296,7 +296,7 @@ public:
     uint64_t iso_fallbacks() const override { return iso_fallbacks_; }
 
     // ---- per-kernel-group profiling: CUDA events on the launching stream + exact work counts from launch parameters
-    void set_profiling(bool on) override { prof_on_ = on; }
+    void set_profiling(int mode) override { prof_on_ = mode != 0; prof_detail_ = mode == 2; }
     void profile_reset() override { for (auto& e : prof_) { e.launches = 0; e.scopes = 0; e.ms = 0; e.bytes = 0; e.modmul = 0; } }
     std::string profile_json() override {
         prof_collect();
@@ -805,6 +805,8 @@ private:
     struct ProfEntry { std::string name; uint64_t launches = 0, scopes = 0; double ms = 0, bytes = 0, modmul = 0; };
     struct ProfPending { int tag; cudaEvent_t a, b; uint64_t l0, l1; };
     bool prof_on_ = false;
+    bool prof_detail_ = false;   // mode 2: one entry per (kernel group, tree level): "name@L<level>"
+    int prof_level_ = -1;        // tree level the launches being issued belong to (-1: outside the level loop)
     std::vector<ProfEntry> prof_;
     std::vector<ProfPending> pending_;
     std::vector<cudaEvent_t> evpool_;
@@ -822,7 +824,12 @@ private:
         Engine* eng; bool live;
         Scope(Engine* e, const char* name, double bytes, double modmul) : eng(e), live(e->prof_on_) {
             if (!live) return;
-            int tag = eng->prof_tag(name);
+            int tag;
+            if (eng->prof_detail_ && eng->prof_level_ >= 0) {
+                char buf[96];
+                snprintf(buf, sizeof buf, "%s@L%02d", name, eng->prof_level_);
+                tag = eng->prof_tag(buf);
+            } else tag = eng->prof_tag(name);
             eng->prof_[tag].bytes += bytes; eng->prof_[tag].modmul += modmul; eng->prof_[tag].scopes += 1;
             ProfPending p; p.tag = tag; p.a = eng->get_event(); p.b = eng->get_event(); p.l0 = eng->launches_; p.l1 = 0;
             cudaEventRecord(p.a, eng->st_);
@@ -1255,6 +1262,8 @@ private:
             ntt(false, EB[0], B[0], 1, 1, nullptr, 0, 0, 1, (size_t)nt * node_max[0], cnt_of(0), (int)node_max[0], (size_t)present[0]);
         }
         for (int l = 0; l < L; ++l) {
+            prof_level_ = l;
+            struct LevelReset { int& v; ~LevelReset() { v = -1; } } level_reset{prof_level_};
             const int t = l + 1;
             const size_t m = (size_t)1 << l, Tn = 2 * m;
             const size_t nodes = node_max[l], merges = node_max[l + 1];

@@ -76,7 +76,8 @@ uint64_t eagen_launch_count(const eagen_ctx* ctx);
 uint64_t eagen_fallback_count(const eagen_ctx* ctx);
 
 /* per-kernel-group profiling (CUDA events on the launching stream + exact byte / modmul counts from the launch
- * parameters).  eagen_profile_json writes a JSON array [{"kernel", "launches", "scopes", "ms", "bytes", "modmul"}, ...]. */
+ * parameters).  eagen_profile_json writes a JSON array [{"kernel", "launches", "scopes", "ms", "bytes", "modmul"}, ...].
+ * on = 0 off, 1 one entry per kernel group, 2 additionally split by tree level ("group@L07": the merge that builds level 8). */
 int eagen_set_profiling(eagen_ctx* ctx, int on);
 /* integer-pipe roofline denominators measured on this device: which = 0 -> dependent-free 32-bit IMAD per second,
  * which = 1 -> base-field Montgomery products per second in a register-resident loop (ceiling of the field code) */

@@ -105,16 +105,25 @@ struct Pallas {
     typedef PallasFp BaseP; typedef PallasFq ScalarP;
     static Fe<BaseP> a() { return Fe<BaseP>::zero(); }
     static Fe<BaseP> b() { return Fe<BaseP>::from_i64(5); }
+    // published generator of the curve (synthetic inputs only; pinned in tests/test_oracle_properties.py)
+    static Fe<BaseP> gx() { static constexpr u64 t[4] = EAGEN_PALLAS_GX_MONT; return Fe<BaseP>::from_raw(t); }
+    static Fe<BaseP> gy() { static constexpr u64 t[4] = EAGEN_PALLAS_GY_MONT; return Fe<BaseP>::from_raw(t); }
 };
 struct Vesta {
     typedef PallasFq BaseP; typedef PallasFp ScalarP;
     static Fe<BaseP> a() { return Fe<BaseP>::zero(); }
     static Fe<BaseP> b() { return Fe<BaseP>::from_i64(5); }
+    // published generator of the curve (synthetic inputs only; pinned in tests/test_oracle_properties.py)
+    static Fe<BaseP> gx() { static constexpr u64 t[4] = EAGEN_VESTA_GX_MONT; return Fe<BaseP>::from_raw(t); }
+    static Fe<BaseP> gy() { static constexpr u64 t[4] = EAGEN_VESTA_GY_MONT; return Fe<BaseP>::from_raw(t); }
 };
 struct Grumpkin {
     typedef Bn256Fr BaseP; typedef Bn256Fq ScalarP;
     static Fe<BaseP> a() { return Fe<BaseP>::zero(); }
     static Fe<BaseP> b() { return Fe<BaseP>::from_i64(-17); }
+    // published generator of the curve (synthetic inputs only; pinned in tests/test_oracle_properties.py)
+    static Fe<BaseP> gx() { static constexpr u64 t[4] = EAGEN_GRUMPKIN_GX_MONT; return Fe<BaseP>::from_raw(t); }
+    static Fe<BaseP> gy() { static constexpr u64 t[4] = EAGEN_GRUMPKIN_GY_MONT; return Fe<BaseP>::from_raw(t); }
 };
 
 }  // namespace oracle

@@ -161,6 +161,48 @@ template <class C> int eval_fn(const u64* a, size_t la, const u64* b, size_t lb,
     std::memcpy(out, v.v, 32);
     return 0;
 }
+
+// Synthetic inputs of SURVEY.md section 8d as the product's k_synth_inputs defines them (halo2-liam-eagen-msm_b200/csrc/kernels.cuh):
+// scalar_j = SplitMix64 draws below 2^bits (2^bits <= isqrt(order)), P_j = (a + j*b) * G for seed-derived odd 64-bit a, b.
+// The oracle emits the points affine (z = 1); every consumer of the path is invariant under the Jacobian representative
+// (SURVEY.md section 8c), so the GPU's triples with non-trivial z describe the same inputs (pinned by a -m gpu test).
+inline u64 splitmix64(u64& s) {
+    s += 0x9E3779B97F4A7C15ull;
+    u64 z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+template <class C> void synth_inputs(u64 seed, size_t n, u64* scalars, u64* pts) {
+    typedef Fe<typename C::ScalarP> S;
+    typedef Point<C> Pt;
+    U256 sq = isqrt(order<typename C::ScalarP>());
+    int bits = 255;
+    while (bits > 0 && !((sq.w[bits / 64] >> (bits % 64)) & 1)) --bits;   // 2^bits <= isqrt(order): 127 on Pasta, 126 on Grumpkin
+    for (size_t j = 0; j < n; ++j) {
+        u64 st = seed ^ (0xD1B54A32D192ED03ull * (u64)(j + 1));
+        u64 c[4] = {0, 0, 0, 0};
+        c[0] = splitmix64(st);
+        c[1] = splitmix64(st) >> (128 - bits);
+        S m = S::from_canonical(c);
+        std::memcpy(scalars + 4 * j, m.v, 32);
+    }
+    u64 s2 = seed;
+    const u64 a = splitmix64(s2) | 1, b = splitmix64(s2) | 1;
+    const Pt G = Pt::from_affine(C::gx(), C::gy());
+    const Pt D = G.mul_limbs(&b, 1);
+    Pool::instance().parallel_for(n, [&](size_t lo, size_t hi) {
+        // k = a + lo*b as a 128-bit integer, then one addition of D per point
+        unsigned __int128 k = (unsigned __int128)a + (unsigned __int128)lo * b;
+        u64 kl[2] = {(u64)k, (u64)(k >> 64)};
+        Pt acc = G.mul_limbs(kl, 2);
+        for (size_t j = lo; j < hi; ++j) {
+            Pt q = acc.normalized();
+            std::memcpy(pts + 12 * j, q.x.v, 32); std::memcpy(pts + 12 * j + 4, q.y.v, 32); std::memcpy(pts + 12 * j + 8, q.z.v, 32);
+            acc = acc + D;
+        }
+    });
+}
 }  // namespace
 
 #define DISPATCH_CURVE(curve, EXPR)                                        \
@@ -228,6 +270,8 @@ int oracle_eval_function(int curve, const u64* a, size_t la, const u64* b, size_
     try { int r = 0; DISPATCH_CURVE(curve, r = eval_fn<C>(a, la, b, lb, pt, out)); return r; }
     catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
+
+int oracle_synth_inputs(int curve, u64 seed, size_t n, u64* scalars, u64* pts) { GUARD(DISPATCH_CURVE(curve, synth_inputs<C>(seed, n, scalars, pts))) }
 
 int oracle_lhs_witness(int curve, const u64* scalars, const u64* pts, size_t n, uint8_t base, int with_functions, void** handle) {
     GUARD(DISPATCH_CURVE(curve, *handle = run_lhs<C>(scalars, pts, n, base, with_functions)))

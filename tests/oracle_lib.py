@@ -203,6 +203,14 @@ class Result:
         L.oracle_result_free(h)
 
 
+def synth_inputs(curve_id, seed, n):
+    """the product's synthetic inputs (k_synth_inputs) restated on the CPU: (n,4) scalars, (n,12) points with z = 1"""
+    S = np.zeros((n, 4), dtype=np.uint64)
+    P = np.zeros((n, 12), dtype=np.uint64)
+    _chk(lib().oracle_synth_inputs(curve_id, C.c_uint64(seed), C.c_size_t(n), _p64(S), _p64(P)))
+    return S, P
+
+
 def lhs_witness(curve_id, scalars, pts, base, with_functions=True):
     scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
     pts = np.ascontiguousarray(pts, dtype=np.uint64)
