@@ -58,7 +58,7 @@ class ClockSampler:
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -104,23 +104,22 @@ def oracle_sample_step(oracle_lib, eg_inputs, log_n, curve_id=0):
     return time.perf_counter() - t0
 
 
-def cpu_inputs(log_n):
-    """synthetic inputs for the CPU legs without touching the GPU product: same family (scalars < 2^127, P_j = P_0 + j*D)"""
-    import numpy as np
-    import oracle_lib
-    import pyref
-    cv = pyref.Curve("pallas")
-    rng = pyref.SplitMix64(0xEA6E0002)
-    p0, dl = pyref.random_point(rng, cv), pyref.random_point(rng, cv)
-    pts = [p0]
-    for _ in range((1 << log_n) - 1):
-        pts.append(cv.add(pts[-1], dl))
-    sc = [rng.next_bits(2) >> 1 for _ in pts]
-    return oracle_lib.pack_felts(sc, cv.q), oracle_lib.pack_points(pts, cv.p)
+def full_size_cpu_record():
+    """the one-off full-size oracle run (tools/golden_full_size.py): seconds, threads, points/s at 2^20 -- quoted beside the bounded samples"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_cpu_2p20.json")) as f:
+            r = json.load(f)
+        return "one-off FULL 2^%d run of the same oracle: %.0f s on %d threads = %.0f points/s (%s; profiles/r02_cpu_2p20.json)" % (
+            r["log_n"], r["oracle_seconds"], r["threads"], r["points_per_second"], r.get("host", "?"))
+    except Exception:
+        return "no full-size CPU record committed"
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the Rust crate cannot be built here) on all host cores"""
+    """--impl reference: the reference's CPU algorithm (oracle port; the Rust crate cannot be built here) on all host cores.
+    A step is the FULL compute_lhs_witness (all d divisor witnesses) on 2^ref_log_n points of the same generator; the size is
+    BASELINE config 2 (2^16) unless K steps of it would not fit the time budget, in which case it is reduced -- and the line's
+    config.workload always names the size that actually ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -128,22 +127,31 @@ def run_reference(args):
     oracle_lib.lib()
     cores = os.cpu_count() or 1
     oracle_lib.set_threads(cores)
-    log_n = args.ref_log_n
     dd = oracle_lib.num_digits(0, BASE)
-    inputs = cpu_inputs(log_n)
+    # probe the host's rate on 2^12 points, then size the step: per-point cost grows like log^2 n
+    probe_n = 12
+    S, P = oracle_lib.synth_inputs(0, 0xEA6E0002, 1 << max(args.ref_log_n, probe_n))
+    t_probe = oracle_sample_step(oracle_lib, (S, P), probe_n)
+    log_n = args.ref_log_n
+    def est(ln):
+        return t_probe * (1 << (ln - probe_n)) * (ln / float(probe_n)) ** 2 * 0.35   # threads are used better on larger trees
+    while log_n > probe_n and est(log_n) * max(args.steps, 1) > args.ref_budget_s:
+        log_n -= 1
     for _ in range(args.warmup):
-        oracle_sample_step(oracle_lib, inputs, max(log_n - 3, 4))
-    t = [oracle_sample_step(oracle_lib, inputs, log_n) for _ in range(args.steps)]
+        oracle_sample_step(oracle_lib, (S, P), max(log_n - 3, 4))
+    t = [oracle_sample_step(oracle_lib, (S, P), log_n) for _ in range(args.steps)]
     total = sum(t)
     value = (1 << log_n) * args.steps / total
-    sample = "full compute_lhs_witness (56 divisor witnesses) on 2^%d Pallas points per step, %d threads; samples of 2^11 .. 2^14 points all measure " \
-             "1.7-1.9 k points/s on 16 cores (more merge levels per point, better thread utilisation)" % (log_n, cores)
+    sample = "full compute_lhs_witness (%d divisor witnesses) on 2^%d Pallas points per step, %d threads, %.1f s per step; %s" % (
+        dd, log_n, cores, total / args.steps, full_size_cpu_record())
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (256-bit Montgomery)",
-        "data": "synthetic", "config": {"workload": "%s MSM witness 2^%d points per GPU (%d total), base 5, d=%d, canonical (a,b) for all %d digit positions"
-                                                 % (args.curve.capitalize(), args.log_n, (1 << args.log_n) * max(args.gpus, 1), dd, dd),
-                                     "reference_sample": "bounded CPU step: 2^%d points of the same workload" % log_n},
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64x4 (256-bit Montgomery, CPU)",
+        "data": "synthetic",
+        "config": {"workload": "Pallas MSM witness 2^%d points per step on the HOST CPU (%d threads), base 5, d=%d, canonical (a,b) for all %d digit positions "
+                               "-- a bounded sample of the GPU arm's 2^%d-point workload (per-point CPU cost grows ~log^2 n, so the full-size CPU rate is lower: see cpu_baseline.sample)"
+                               % (log_n, cores, dd, dd, args.log_n),
+                   "reference_sample_log_n": log_n, "gpu_arm_log_n": args.log_n},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -158,7 +166,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--log-n", type=int, default=20, help="points per GPU = 2^log_n")
-    ap.add_argument("--ref-log-n", type=int, default=13, help="points per CPU reference step (about 5 s per step on 16 cores)")
+    ap.add_argument("--ref-log-n", type=int, default=16, help="points per CPU reference step: BASELINE config 2 (about 35 s per step on 16 cores)")
+    ap.add_argument("--ref-budget-s", type=float, default=400.0, help="the reference arm shrinks its step until K steps fit this many seconds")
     ap.add_argument("--cpu-log-n", type=int, default=14, help="points of the cpu_baseline sample (about 12 s on 16 cores)")
     ap.add_argument("--curve", default="pallas", choices=["pallas", "vesta", "grumpkin"],
                     help="BASELINE config 4 is --curve vesta --log-n 21 under torchrun with 8 ranks (2^24 points)")
@@ -311,8 +320,7 @@ def main():
         sec = oracle_sample_step(oracle_lib, (S, P), args.cpu_log_n, eg.CURVE_IDS[args.curve])
         cpu = {"value": (1 << args.cpu_log_n) / sec, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "oracle (C++ restatement of the reference algorithm; the Rust crate cannot be built here) on the first 2^%d points of the same "
-                         "workload, all 56 divisor witnesses, %.1f s; samples of 2^11 .. 2^14 points all measure 1.7-1.9 k points/s on 16 cores"
-                         % (args.cpu_log_n, sec)}
+                         "workload, all 56 divisor witnesses, %.1f s on %d threads; %s" % (args.cpu_log_n, sec, cores, full_size_cpu_record())}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,

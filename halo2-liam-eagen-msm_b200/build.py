@@ -7,7 +7,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libeagen_msm.so")
+OUT = os.environ.get("EAGEN_OUT", os.path.join(HERE, "libeagen_msm.so"))
+OBJ_SUFFIX = os.environ.get("EAGEN_OBJ_SUFFIX", "")   # variant builds keep their own objects (tools/variant.sh)
 SOURCES = ["capi.cu", "engine_pallas.cu", "engine_vesta.cu", "engine_grumpkin.cu"]
 HEADERS = ["field.cuh", "curve.cuh", "kernels.cuh", "engine.cuh", "eagen_params.h", os.path.join("..", "..", "include", "eagen_msm.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -28,7 +29,7 @@ def build(force=False, verbose=False):
     jobs = []
     for s in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(CSRC, s.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, s.replace(".cu", OBJ_SUFFIX + ".o"))
         objs.append(obj)
         if force or stale(obj, [src] + hdrs):
             jobs.append((src, obj))

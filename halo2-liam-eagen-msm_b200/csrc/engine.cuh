@@ -87,6 +87,27 @@ struct BufPool {
     }
 };
 
+// Pinned host staging ring for the small per-call parameter tables (level counts, position maps, error flags): an asynchronous
+// copy from PAGEABLE memory makes the driver synchronise the stream first, a copy from pinned memory does not.  Every public call
+// ends with a stream synchronisation and stages far less than the ring holds, so a wrapped allocation never overlaps data in flight.
+struct PinnedRing {
+    char* p = nullptr;
+    size_t cap = 0, off = 0;
+    void init(size_t bytes) {
+        if (cudaHostAlloc((void**)&p, bytes, cudaHostAllocDefault) != cudaSuccess) { p = nullptr; throw CudaError{"cudaHostAlloc of the staging ring failed", EAGEN_E_CUDA}; }
+        cap = bytes;
+    }
+    void* take(size_t bytes) {
+        bytes = (bytes + 63) & ~(size_t)63;
+        if (bytes > cap) throw CudaError{"staging ring too small", EAGEN_E_CUDA};
+        if (off + bytes > cap) off = 0;
+        void* r = p + off;
+        off += bytes;
+        return r;
+    }
+    ~PinnedRing() { if (p) cudaFreeHost(p); }
+};
+
 // ---- result handle -------------------------------------------------------------------------------------
 struct ResultImpl {
     std::shared_ptr<BufPool> pool;       // buffers go back to the owning context's pool when the result is freed
@@ -274,6 +295,9 @@ public:
         EAGEN_CUDA(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev_));
         EAGEN_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
         EAGEN_CUDA(cudaStreamCreateWithFlags(&cst_, cudaStreamNonBlocking));
+        EAGEN_CUDA(cudaStreamCreateWithFlags(&pst_, cudaStreamNonBlocking));
+        ls_ = st_;
+        ring_.init((size_t)8 << 20);
         EAGEN_CUDA(cudaMalloc(&d_err_, sizeof(int)));
         EAGEN_CUDA(cudaMemsetAsync(d_err_, 0, sizeof(int), st_));
         EAGEN_CUDA(cudaEventCreate(&ev0_));
@@ -288,7 +312,9 @@ public:
         cudaStreamSynchronize(st_);
         cudaFree(d_err_); cudaFree(d_one_);
         cudaEventDestroy(ev0_); cudaEventDestroy(ev1_);
+        for (cudaEvent_t e : sync_events_) cudaEventDestroy(e);
         cudaStreamDestroy(cst_);
+        cudaStreamDestroy(pst_);
         cudaStreamDestroy(st_);
     }
     int device() const override { return dev_; }
@@ -771,7 +797,7 @@ public:
         F* dp = (F*)in_points_.ensure(std::min(m, batch) * 96);
         Aff* T = (Aff*)tpts_.ensure(std::min(m, batch) * sizeof(Aff));
         F* zs = (F*)den_.ensure(std::min(m, batch) * 32);
-        F* X = (F*)wk_.ensure(std::min(m, batch) * len * 32);
+        F* X = (F*)wk_[0].ensure(std::min(m, batch) * len * 32);
         F* part = (F*)binv_.ensure(std::min(m, batch) * nf * (size_t)nchunks * 64);
         F* dout = (F*)oa_.ensure(nf * std::min(m, batch) * 32);
         std::vector<uint64_t> tmp(nf * std::min(m, batch) * 4);
@@ -803,7 +829,7 @@ public:
 
 private:
     struct ProfEntry { std::string name; uint64_t launches = 0, scopes = 0; double ms = 0, bytes = 0, modmul = 0; };
-    struct ProfPending { int tag; cudaEvent_t a, b; uint64_t l0, l1; };
+    struct ProfPending { int tag; cudaEvent_t a, b; uint64_t l0, l1; cudaStream_t st; };
     bool prof_on_ = false;
     bool prof_detail_ = false;   // mode 2: one entry per (kernel group, tree level): "name@L<level>"
     int prof_level_ = -1;        // tree level the launches being issued belong to (-1: outside the level loop)
@@ -832,14 +858,15 @@ private:
             } else tag = eng->prof_tag(name);
             eng->prof_[tag].bytes += bytes; eng->prof_[tag].modmul += modmul; eng->prof_[tag].scopes += 1;
             ProfPending p; p.tag = tag; p.a = eng->get_event(); p.b = eng->get_event(); p.l0 = eng->launches_; p.l1 = 0;
-            cudaEventRecord(p.a, eng->st_);
+            p.st = eng->ls_;
+            cudaEventRecord(p.a, p.st);
             eng->pending_.push_back(p);
             idx = eng->pending_.size() - 1;
         }
         ~Scope() {
             if (!live) return;
             ProfPending& p = eng->pending_[idx];
-            cudaEventRecord(p.b, eng->st_);
+            cudaEventRecord(p.b, p.st);
             p.l1 = eng->launches_;
         }
         size_t idx = 0;
@@ -847,6 +874,7 @@ private:
     void prof_collect() {
         if (pending_.empty()) return;
         cudaStreamSynchronize(st_);
+        cudaStreamSynchronize(pst_);
         for (auto& p : pending_) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) prof_[p.tag].ms += ms;
@@ -860,8 +888,22 @@ private:
     int sm_count_ = 148;
     std::shared_ptr<BufPool> pool_ = std::make_shared<BufPool>();
     cudaStream_t st_ = nullptr, cst_ = nullptr;  // compute stream, copy stream (streamed results)
+    cudaStream_t pst_ = nullptr;                 // side stream: the point pyramid (output points, lines, descriptors) runs ahead of the polynomial levels
+    cudaStream_t ls_ = nullptr;                  // stream launch() / Scope / batch_invert currently issue to (st_ unless inside OnStream)
+    std::vector<cudaEvent_t> sync_events_;       // timing-disabled events for cross-stream ordering, reused across calls
+    cudaEvent_t sync_event(size_t i) {
+        while (sync_events_.size() <= i) { cudaEvent_t e; EAGEN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); sync_events_.push_back(e); }
+        return sync_events_[i];
+    }
+    struct OnStream {   // RAII: route launches to another stream
+        Engine* eng; cudaStream_t prev;
+        OnStream(Engine* e, cudaStream_t s) : eng(e), prev(e->ls_) { e->ls_ = s; }
+        ~OnStream() { eng->ls_ = prev; }
+    };
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     int* d_err_ = nullptr;
+    int last_tree_err_ = 0;
+    PinnedRing ring_;
     int* d_one_ = nullptr;
     uint64_t launches_ = 0;
     uint64_t iso_fallbacks_ = 0;   // trees rebuilt on an isomorphic curve after a domain collision
@@ -870,7 +912,7 @@ private:
     DevBuf in_scalars_, in_points_, planes_, rows_, table_, sums_, partials_, carries_, carries_proj_;
     DevBuf cnt_, tree_n_, tree_of_pos_, tpts_, isodeg_;
     std::unique_ptr<Scope> prof_scope_;
-    DevBuf ptlev_, lvlcnt_, a_[2], b_[2], ea_, eb_, oa_, ob_, wk_, top_, twist_, den_, binv_, desc_, tops_, lead_;
+    DevBuf pden_, pbinv_, ptlev_, lvlcnt_, a_[2], b_[2], ea_, eb_, oa_, ob_, wk_[2], top_, twist_, den_, binv_, desc_, tops_, lead_;
 
     void use() { EAGEN_CUDA(cudaSetDevice(dev_)); }
 
@@ -878,23 +920,24 @@ private:
     void launch(K kernel, size_t work, int threads, Args... args) {
         if (work == 0) return;
         size_t blocks = (work + threads - 1) / threads;
-        kernel<<<(unsigned)blocks, threads, 0, st_>>>(args...);
+        kernel<<<(unsigned)blocks, threads, 0, ls_>>>(args...);
         ++launches_;
         EAGEN_CUDA(cudaGetLastError());
     }
     template <class K, class... Args>
     void launch2d(K kernel, dim3 grid, int threads, Args... args) {
         if (grid.x == 0 || grid.y == 0) return;
-        kernel<<<grid, threads, 0, st_>>>(args...);
+        kernel<<<grid, threads, 0, ls_>>>(args...);
         ++launches_;
         EAGEN_CUDA(cudaGetLastError());
     }
 
     void sync_check() {
+        int* herr = (int*)ring_.take(sizeof(int));
+        EAGEN_CUDA(cudaMemcpyAsync(herr, d_err_, sizeof(int), cudaMemcpyDeviceToHost, st_));
         EAGEN_CUDA(cudaStreamSynchronize(st_));
         prof_collect();
-        int e = 0;
-        EAGEN_CUDA(cudaMemcpy(&e, d_err_, sizeof(int), cudaMemcpyDeviceToHost));
+        const int e = *herr;
         if (e) {
             EAGEN_CUDA(cudaMemset(d_err_, 0, sizeof(int)));
             if (e & KERR_RANGE) throw StatusError{EAGEN_E_RANGE, "scalar out of range: must be < isqrt(order)+2"};
@@ -921,14 +964,19 @@ private:
         F* xt = (F*)xt_.ensure(2 * cnt * 32);
         F* gt = (F*)gt_.ensure(2 * cnt * 32);
         launch(k_gen_points<CC>, 2 * cnt, 256, (const F*)f, t, xt, gt);
+        F* tws = (F*)twist_.ensure(cnt * 32);
+        launch(k_gen_twist_all<FB>, cnt, 256, (const F*)f, t, tws);
         tw_max_ = t;
     }
     const F* xtab(int t) { return xt_.as<F>() + ((size_t)1 << t); }
     const F* gtab(int t) { return gt_.as<F>() + ((size_t)1 << t); }
+    const F* twist_tab(int l) { return twist_.as<F>() + ((size_t)1 << l); }   // coset pre-multipliers of the level with m = 2^l
     const F* tw(bool inverse, int t) { return (inverse ? tw_inv_.as<F>() : tw_fwd_.as<F>()) + ((size_t)1 << (t - 1)); }
 
-    // in-place batched inversion of M elements (zeros stay zero)
-    void batch_invert(F* x, size_t M) {
+    // in-place batched inversion of M elements (zeros stay zero); launches go to the current launch stream, `scratch` must not be
+    // shared with a batch in flight on another stream
+    void batch_invert(F* x, size_t M) { batch_invert(x, M, binv_); }
+    void batch_invert(F* x, size_t M, DevBuf& scratch_buf) {
         if (M == 0) return;
         Scope ps(this, "batch_invert", 160.0 * M * (1.0 + 1.0 / (BINV_G - 1)), 3.0 * M * (1.0 + 1.0 / (BINV_G - 1)));
         // level sizes
@@ -936,7 +984,7 @@ private:
         while (sz.back() > 1024) sz.push_back((sz.back() + BINV_G - 1) / BINV_G);
         size_t scratch = 0;
         for (size_t l = 0; l + 1 < sz.size(); ++l) scratch += sz[l] + sz[l + 1];
-        F* s = (F*)binv_.ensure(std::max<size_t>(scratch, 1) * 32);
+        F* s = (F*)scratch_buf.ensure(std::max<size_t>(scratch, 1) * 32);
         std::vector<F*> xs{x}, prefs;
         F* cur = s;
         for (size_t l = 0; l + 1 < sz.size(); ++l) { prefs.push_back(cur); cur += sz[l]; xs.push_back(cur); cur += sz[l + 1]; }
@@ -947,26 +995,32 @@ private:
             launch(k_binv_down<FB>, sz[l + 1], 128, xs[l], (const F*)prefs[l], (const F*)xs[l + 1], sz[l], sz[l + 1]);
     }
 
-    // batched transform of n_tr arrays of size 2^t living in `data`; optional compact gather / scatter
-    void ntt(bool inverse, F* data, const F* src, size_t src_stride, int src_len, F* dst, size_t dst_stride, int dst_len,
-             int t, size_t n_tr, const int* counts, int node_max, size_t n_present = (size_t)-1,
-             const F* twist = nullptr, const F* sub_top = nullptr, size_t dst_off = 0) {
+    // One polynomial family of a batched transform: n_tr arrays of size 2^t in `data` (the in-place workspace of the middle
+    // passes), optionally gathered from compact slots by the first pass (`src`, zero padded beyond src_len) and scattered back
+    // into compact slots by the last one (`dst`).
+    struct NttJob {
+        F* data; const F* src; size_t src_stride; int src_len; F* dst; size_t dst_stride; int dst_len; const F* sub_top;
+    };
+    // batched transform of up to two families (the a and b polynomials of a level) per launch: blockIdx.y selects the family
+    void ntt(bool inverse, const NttJob* jobs, int njobs, int t, size_t n_tr, const int* counts, int node_max, size_t n_present = (size_t)-1,
+             const F* twist = nullptr, size_t dst_off = 0) {
         if (n_present == (size_t)-1) n_present = n_tr;
+        std::vector<std::pair<int, int>> plan = ntt_plan(t);
         {   // algorithmic work: every present element is read and written once per pass, t/2 modmul per element in total
-            std::vector<std::pair<int, int>> pl = ntt_plan(t);
             double el = (double)n_present * (double)((size_t)1 << t);
-            double bytes = 64.0 * el * pl.size();
-            if (src) bytes -= 32.0 * el - 32.0 * (double)n_present * src_len;
-            if (dst) bytes -= 32.0 * el - 32.0 * (double)n_present * dst_len;
+            double bytes = 0;
+            for (int j = 0; j < njobs; ++j) {
+                bytes += 64.0 * el * plan.size();
+                if (jobs[j].src) bytes -= 32.0 * el - 32.0 * (double)n_present * jobs[j].src_len;
+                if (jobs[j].dst) bytes -= 32.0 * el - 32.0 * (double)n_present * jobs[j].dst_len;
+            }
             prof_scope_.reset(new Scope(this, inverse ? "ntt_inverse" : "ntt_forward", bytes,
-                                        el * t / 2.0 - (t >= 2 ? 0.75 * el : 0.5 * el) + (twist ? el : 0.0)));  // stages 0/1 have w = 1
+                                        njobs * (el * t / 2.0 - (t >= 2 ? 0.75 * el : 0.5 * el) + (twist ? el : 0.0))));  // stages 0/1 have w = 1
         }
         struct Closer { std::unique_ptr<Scope>& s; ~Closer() { s.reset(); } } closer{prof_scope_};
         NttPass<FB> a;
-        a.data = data; a.tw = tw(inverse, t); a.counts = counts; a.node_max = node_max;
+        a.counts = counts; a.node_max = node_max;
         a.total = n_tr << t; a.t = t;
-        a.src_stride = src_stride; a.src_len = src_len; a.dst_stride = dst_stride; a.dst_len = dst_len;
-        std::vector<std::pair<int, int>> plan = ntt_plan(t);
         if (inverse) std::reverse(plan.begin(), plan.end());
         size_t tiles = (a.total + NTT_TILE - 1) / NTT_TILE;
         for (size_t p = 0; p < plan.size(); ++p) {
@@ -974,16 +1028,28 @@ private:
             // w_T^(j 2^(t-1-s)) = w_{2^(s+1)}^j: the last (contiguous) pass only needs the 2^k-point table, which stays in L1
             a.tw_t = a.s_lo == 0 ? a.s_hi + 1 : t;
             a.tw = tw(inverse, a.tw_t);
-            a.src = (p == 0) ? src : nullptr;
             a.twist = (p == 0) ? twist : nullptr;
-            a.dst = (p + 1 == plan.size()) ? dst : nullptr;
-            a.sub_top = (p + 1 == plan.size()) ? sub_top : nullptr;
             a.dst_off = dst_off;
-            if (inverse) k_ntt_pass<FB, true><<<(unsigned)tiles, NTT_THREADS, 0, st_>>>(a);
-            else k_ntt_pass<FB, false><<<(unsigned)tiles, NTT_THREADS, 0, st_>>>(a);
+            for (int j = 0; j < 2; ++j) {
+                const NttJob& jb = jobs[j < njobs ? j : 0];
+                NttSide<FB>& sd = a.side[j];
+                sd.data = jb.data;
+                sd.src = (p == 0) ? jb.src : nullptr; sd.src_stride = jb.src_stride; sd.src_len = jb.src_len;
+                sd.dst = (p + 1 == plan.size()) ? jb.dst : nullptr; sd.dst_stride = jb.dst_stride; sd.dst_len = jb.dst_len;
+                sd.sub_top = (p + 1 == plan.size()) ? jb.sub_top : nullptr;
+            }
+            dim3 grid((unsigned)tiles, (unsigned)njobs);
+            if (inverse) k_ntt_pass<FB, true><<<grid, NTT_THREADS, 0, st_>>>(a);
+            else k_ntt_pass<FB, false><<<grid, NTT_THREADS, 0, st_>>>(a);
             ++launches_;
             EAGEN_CUDA(cudaGetLastError());
         }
+    }
+    // single-family convenience form
+    void ntt(bool inverse, F* data, const F* src, size_t src_stride, int src_len, F* dst, size_t dst_stride, int dst_len,
+             int t, size_t n_tr, const int* counts, int node_max) {
+        NttJob jb{data, src, src_stride, src_len, dst, dst_stride, dst_len, nullptr};
+        ntt(inverse, &jb, 1, t, n_tr, counts, node_max);
     }
 
     void run_negbase(const Fe<FS>* ds, size_t n, const NegbaseParams& prm, uint8_t* planes, uint8_t* rows) {
@@ -1103,8 +1169,11 @@ private:
             uint32_t g1 = std::min(pos_end, g0 + sizes[gi]), nt = g1 - g0;
             std::vector<int> map(d, -1), cnts(nt);
             for (uint32_t p = g0; p < g1; ++p) { map[p] = (int)(p - g0); cnts[p - g0] = hn[p]; }
-            EAGEN_CUDA(cudaMemcpyAsync(tree_of_pos, map.data(), (size_t)d * sizeof(int), cudaMemcpyHostToDevice, st_));
-            EAGEN_CUDA(cudaStreamSynchronize(st_));  // `map` is a stack temporary
+            {
+                int* stage = (int*)ring_.take((size_t)d * sizeof(int));
+                std::memcpy(stage, map.data(), (size_t)d * sizeof(int));
+                EAGEN_CUDA(cudaMemcpyAsync(tree_of_pos, stage, (size_t)d * sizeof(int), cudaMemcpyHostToDevice, st_));
+            }
             Aff* T = (Aff*)tpts_.ensure((size_t)nt * nmax * sizeof(Aff));
             {
                 Scope ps(this, "scatter_points", (double)nt * ((double)n + 128.0 * (double)nmax), 0.0);
@@ -1129,14 +1198,14 @@ private:
     }
 
     size_t pooled_bytes() const {
-        return tpts_.cap + ptlev_.cap + a_[0].cap + a_[1].cap + b_[0].cap + b_[1].cap + ea_.cap + eb_.cap + oa_.cap + ob_.cap + wk_.cap + den_.cap + binv_.cap + desc_.cap;
+        return tpts_.cap + ptlev_.cap + pden_.cap + pbinv_.cap + a_[0].cap + a_[1].cap + b_[0].cap + b_[1].cap + ea_.cap + eb_.cap + oa_.cap + ob_.cap + wk_[0].cap + wk_[1].cap + den_.cap + binv_.cap + desc_.cap;
     }
     // working-set estimate per tree of n points (bytes)
     static size_t tree_bytes(size_t n) {
         size_t lc = (n + 1) / 2;
         size_t L = (size_t)ceil_log2(lc);
         size_t pad = lc + ((size_t)1 << L) + 8;  // slack for the +1 slots and the top levels
-        return n * 64 + 2 * lc * 64 + pad * 32 * (4 + 8 + 2 + 3) + lc * sizeof(MergeDesc<FB>) / 2 + 4096;
+        return n * 64 + 2 * lc * 64 + pad * 32 * (4 + 8 + 3 + 3) + lc * (sizeof(MergeDesc<FB>) + 32 + 32 * 3 / 2) + 4096;
     }
 
     static F iso_gshift(uint32_t u) {   // (u^6 - 1) b
@@ -1153,8 +1222,7 @@ private:
         uint32_t total_u = 1;
         static const uint32_t steps[4] = {2, 3, 5, 7};
         for (int attempt = 0; attempt < 4; ++attempt) {
-            int e = 0;
-            EAGEN_CUDA(cudaMemcpy(&e, d_err_, sizeof(int), cudaMemcpyDeviceToHost));
+            int e = last_tree_err_;   // the device flag as run_trees read it back with its lengths (no extra round trip)
             if (!(e & KERR_COLLISION)) break;
             e &= ~KERR_COLLISION;
             EAGEN_CUDA(cudaMemcpy(d_err_, &e, sizeof(int), cudaMemcpyHostToDevice));
@@ -1202,8 +1270,11 @@ private:
             for (int l = 0; l <= L; ++l) { lv[(size_t)(l + 1) * nt + tr] = c; c = (c + 1) / 2; }
         }
         int* dlv = (int*)lvlcnt_.ensure(lv.size() * sizeof(int));
-        EAGEN_CUDA(cudaMemcpyAsync(dlv, lv.data(), lv.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
-        EAGEN_CUDA(cudaStreamSynchronize(st_));
+        {
+            int* stage = (int*)ring_.take(lv.size() * sizeof(int));
+            std::memcpy(stage, lv.data(), lv.size() * sizeof(int));
+            EAGEN_CUDA(cudaMemcpyAsync(dlv, stage, lv.size() * sizeof(int), cudaMemcpyHostToDevice, st_));
+        }
         auto cnt_of = [&](int level) { return (const int*)(dlv + (size_t)(level + 1) * nt); };
 
         // memory plan
@@ -1226,11 +1297,13 @@ private:
         // first half of level l+1's buffers; W is the in-place workspace of the coset and inverse transforms
         F* EA[2] = {(F*)ea_.ensure(std::max<size_t>(szE, 1) * 32), (F*)oa_.ensure(std::max<size_t>(szE, 1) * 32)};
         F* EB[2] = {(F*)eb_.ensure(std::max<size_t>(szE, 1) * 32), (F*)ob_.ensure(std::max<size_t>(szE, 1) * 32)};
-        F* W = (F*)wk_.ensure(std::max<size_t>(szO, 1) * 32);
+        F* W[2] = {(F*)wk_[0].ensure(std::max<size_t>(szO, 1) * 32), (F*)wk_[1].ensure(std::max<size_t>(szO, 1) * 32)};
         F* TOP = (F*)top_.ensure(std::max<size_t>((size_t)nt * (L ? node_max[1] : 1), 1) * 32);
-        F* TWIST = (F*)twist_.ensure(((size_t)1 << (L > 0 ? L - 1 : 0)) * 32);
         F* den = (F*)den_.ensure(std::max<size_t>(std::max(szO, (size_t)nt * node_max[0]), 1) * 32);
-        MergeDesc<FB>* desc = (MergeDesc<FB>*)desc_.ensure(std::max<size_t>((size_t)nt * (L ? node_max[1] : 1), 1) * sizeof(MergeDesc<FB>));
+        std::vector<size_t> desc_off(L + 1, 0);   // descriptors of every level are kept: the point pyramid runs ahead on its own stream
+        for (int l = 0; l < L; ++l) desc_off[l + 1] = desc_off[l] + (size_t)nt * node_max[l + 1];
+        MergeDesc<FB>* desc_all = (MergeDesc<FB>*)desc_.ensure(std::max<size_t>(desc_off[L], 1) * sizeof(MergeDesc<FB>));
+        F* pden = (F*)pden_.ensure(std::max<size_t>((size_t)nt * node_max[0], 1) * 32);
         if (L) ensure_twiddles(L);
 
         // present nodes per level (exact work counts for the profiler)
@@ -1243,23 +1316,53 @@ private:
             iso_deg = (int*)isodeg_.ensure((size_t)nt * sizeof(int));
             EAGEN_CUDA(cudaMemsetAsync(iso_deg, 0, (size_t)nt * sizeof(int), st_));
         }
-        // level 0: outputs -(P+Q) and the line functions
-        size_t w0 = (size_t)nt * node_max[0];
+        // The point pyramid -- output points -(P+Q) of the leaves, A+B of every merge, the merge descriptors (division roots, lines) --
+        // depends on the lists only, never on the polynomials, and its upper levels are latency bound (a few nodes per tree, one
+        // serial field inversion per batch): it runs on the side stream, ahead of the polynomial levels, with its own scratch.
+        // Event 0: leaves' output points ready; event l + 1: descriptors of the merge that builds level l + 1 ready.
+        const size_t w0 = (size_t)nt * node_max[0];
         {
-            Scope ps(this, "pair_points", present[0] * (128.0 + 32.0), 0.0);
-            launch(k_pair_den<FB>, w0, 256, T, cap, (const int*)dlv, node_max[0], nt, den);
+            EAGEN_CUDA(cudaEventRecord(sync_event(0), st_));          // the lists (and the level counts) are complete on the main stream
+            EAGEN_CUDA(cudaStreamWaitEvent(pst_, sync_event(0), 0));
+            OnStream side(this, pst_);
+            {
+                Scope ps(this, "pair_points", present[0] * (128.0 + 32.0), 0.0);
+                launch(k_pair_den<FB>, w0, 256, T, cap, (const int*)dlv, node_max[0], nt, pden);
+            }
+            batch_invert(pden, w0, pbinv_);
+            {
+                Scope ps(this, "pair_points", present[0] * (128.0 + 32.0 + 64.0), present[0] * 4.0);
+                launch(k_pair_finish<FB>, w0, 256, T, cap, (const int*)dlv, node_max[0], nt, (const F*)pden, 1, PT + pt_off[0]);
+            }
+            EAGEN_CUDA(cudaEventRecord(sync_event(1), pst_));
+            for (int l = 0; l < L; ++l) {
+                const size_t nodes = node_max[l], merges = node_max[l + 1], wm = (size_t)nt * merges;
+                Aff* Pc = PT + pt_off[l];
+                Aff* Pp = PT + pt_off[l + 1];
+                {
+                    Scope ps(this, "pair_points", present[l + 1] * (128.0 + 32.0), 0.0);
+                    launch(k_pair_den<FB>, wm, 256, (const Aff*)Pc, nodes, cnt_of(l), merges, nt, pden);
+                }
+                batch_invert(pden, wm, pbinv_);
+                {
+                    Scope ps(this, "pair_points", present[l + 1] * (128.0 + 32.0 + 64.0 + 192.0 + (double)sizeof(MergeDesc<FB>)), present[l + 1] * (4.0 + 2.0));
+                    launch(k_pair_finish<FB>, wm, 256, (const Aff*)Pc, nodes, cnt_of(l), merges, nt, (const F*)pden, 0, Pp);
+                    launch(k_merge_desc<FB>, wm, 128, (const Aff*)Pc, nodes, cnt_of(l), (const Aff*)Pp, merges, nt, desc_all + desc_off[l], iso_deg);
+                }
+                EAGEN_CUDA(cudaEventRecord(sync_event((size_t)l + 2), pst_));
+            }
         }
-        batch_invert(den, w0);
+        // level 0 on the main stream: the line functions of the leaves
+        EAGEN_CUDA(cudaStreamWaitEvent(st_, sync_event(1), 0));
         {
-            Scope ps(this, "pair_points", present[0] * (128.0 + 32.0 + 64.0 + 128.0 + 64.0 + 96.0), present[0] * (4.0 + 2.0));
-            launch(k_pair_finish<FB>, w0, 256, T, cap, (const int*)dlv, node_max[0], nt, (const F*)den, 1, PT + pt_off[0]);
+            Scope ps(this, "pair_points", present[0] * (128.0 + 64.0 + 96.0), present[0] * 2.0);
             launch(k_leaf_lines<FB>, w0, 256, T, cap, (const int*)dlv, (const Aff*)(PT + pt_off[0]), node_max[0], nt, A[0], B[0], iso_deg);
         }
 
         int cur = 0, e = 0;
         if (L > 0) {  // the leaves' evaluations on the 2-point domain (full forward transform, true coefficients)
-            ntt(false, EA[0], A[0], 2, 2, nullptr, 0, 0, 1, (size_t)nt * node_max[0], cnt_of(0), (int)node_max[0], (size_t)present[0]);
-            ntt(false, EB[0], B[0], 1, 1, nullptr, 0, 0, 1, (size_t)nt * node_max[0], cnt_of(0), (int)node_max[0], (size_t)present[0]);
+            NttJob jl[2] = {{W[0], A[0], 2, 2, EA[0], 2, 2, nullptr}, {W[1], B[0], 1, 1, EB[0], 2, 2, nullptr}};
+            ntt(false, jl, 2, 1, (size_t)nt * node_max[0], cnt_of(0), (int)node_max[0], (size_t)present[0]);
         }
         for (int l = 0; l < L; ++l) {
             prof_level_ = l;
@@ -1269,34 +1372,17 @@ private:
             const size_t nodes = node_max[l], merges = node_max[l + 1];
             const size_t wm = (size_t)nt * merges;
             const double pts = present[l + 1] * (double)Tn;  // evaluation points of this level
-            Aff* Pc = PT + pt_off[l];
-            Aff* Pp = PT + pt_off[l + 1];
-            // output points of the parents and the merge descriptors
-            {
-                Scope ps(this, "pair_points", present[l + 1] * (128.0 + 32.0), 0.0);
-                launch(k_pair_den<FB>, wm, 256, (const Aff*)Pc, nodes, cnt_of(l), merges, nt, den);
-            }
-            batch_invert(den, wm);
-            {
-                Scope ps(this, "pair_points", present[l + 1] * (128.0 + 32.0 + 64.0 + 192.0 + 272.0), present[l + 1] * (4.0 + 5.0));
-                launch(k_pair_finish<FB>, wm, 256, (const Aff*)Pc, nodes, cnt_of(l), merges, nt, (const F*)den, 0, Pp);
-                launch(k_merge_desc<FB>, wm, 128, (const Aff*)Pc, nodes, cnt_of(l), (const Aff*)Pp, merges, nt, F::one(), desc, iso_deg);
-            }
+            const MergeDesc<FB>* desc = desc_all + desc_off[l];
             // Children in the evaluation domain.  Positions [0, m) of each child's 2m-point buffer already hold its values on the
             // m-point domain (written by the previous level's merge); only the odd coset w_T * w_m^k is transformed here:
             // a(x) = sum_{i<m} c_i x^i + c_m x^m and x^m = -1 on the coset, so values = NTT_m(c_i w_T^i) - c_m.
             // Stored coefficients carry the factor s = m of the unscaled inverse transform; the twist table removes it.
             if (l > 0) {
-                {
-                    Scope ps(this, "ntt_forward", (double)m * 64.0, (double)m);
-                    launch(k_gen_twist<FB>, m, 256, tw(false, t), m, half_pow(l), TWIST);
-                }
-                ntt(false, W, A[cur], m + 1, (int)m, EA[e], Tn, (int)m, l, (size_t)nt * nodes, cnt_of(l), (int)nodes, (size_t)present[l],
-                    (const F*)TWIST, (const F*)TOP, m);
-                ntt(false, W, B[cur], m, (int)m, EB[e], Tn, (int)m, l, (size_t)nt * nodes, cnt_of(l), (int)nodes, (size_t)present[l],
-                    (const F*)TWIST, nullptr, m);
+                NttJob jf[2] = {{W[0], A[cur], m + 1, (int)m, EA[e], Tn, (int)m, (const F*)TOP}, {W[1], B[cur], m, (int)m, EB[e], Tn, (int)m, nullptr}};
+                ntt(false, jf, 2, l, (size_t)nt * nodes, cnt_of(l), (int)nodes, (size_t)present[l], twist_tab(l), m);
             }
             // pointwise merge with exact division; parents' evaluations go to the next level's buffers (stride 2T)
+            EAGEN_CUDA(cudaStreamWaitEvent(st_, sync_event((size_t)l + 2), 0));   // this level's descriptors (side stream)
             {
                 Scope ps(this, "merge_den", pts * 64.0, pts * 1.0);
                 launch(k_den<FB>, wm << t, 256, (const MergeDesc<FB>*)desc, wm, t, xtab(t), den, d_err_);
@@ -1312,8 +1398,10 @@ private:
                            (const F*)den, merges, nodes, EA[e ^ 1], EB[e ^ 1], 2 * Tn, F::zero());
             }
             // back to coefficients (unscaled: stored = T * true), compact parent slots
-            ntt(true, W, EA[e ^ 1], 2 * Tn, (int)Tn, A[cur ^ 1], Tn + 1, (int)Tn, t, wm, cnt_of(l + 1), (int)merges, (size_t)present[l + 1]);
-            ntt(true, W, EB[e ^ 1], 2 * Tn, (int)Tn, B[cur ^ 1], Tn, (int)Tn, t, wm, cnt_of(l + 1), (int)merges, (size_t)present[l + 1]);
+            {
+                NttJob ji[2] = {{W[0], EA[e ^ 1], 2 * Tn, (int)Tn, A[cur ^ 1], Tn + 1, (int)Tn, nullptr}, {W[1], EB[e ^ 1], 2 * Tn, (int)Tn, B[cur ^ 1], Tn, (int)Tn, nullptr}};
+                ntt(true, ji, 2, t, wm, cnt_of(l + 1), (int)merges, (size_t)present[l + 1]);
+            }
             {
                 Scope ps(this, "merge_fixup", present[l + 1] * (6 * 32.0 + 96.0), present[l + 1] * 7.0);
                 F kc = l == 0 ? F::one() : half_pow(2 * l);
@@ -1372,7 +1460,10 @@ private:
             EAGEN_CUDA(cudaMemcpyAsync(res->A.as<F>() + slot * res->a_stride, A[cur] + (size_t)tr * ra, ra * 32, cudaMemcpyDeviceToDevice, st_));
             EAGEN_CUDA(cudaMemcpyAsync(res->B.as<F>() + slot * res->b_stride, B[cur] + (size_t)tr * rb, rb * 32, cudaMemcpyDeviceToDevice, st_));
         }
+        int* herr = (int*)ring_.take(sizeof(int));
+        EAGEN_CUDA(cudaMemcpyAsync(herr, d_err_, sizeof(int), cudaMemcpyDeviceToHost, st_));
         EAGEN_CUDA(cudaStreamSynchronize(st_));
+        last_tree_err_ = *herr;
         for (int tr = 0; tr < nt; ++tr) {
             size_t slot = first_slot + (dir > 0 ? (size_t)tr : (size_t)(nt - 1 - tr));
             res->la[slot] = htops[tr]; res->lb[slot] = htops[nt + tr];

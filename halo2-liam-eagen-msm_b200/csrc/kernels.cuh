@@ -624,14 +624,13 @@ enum : uint32_t { MERGE_ABSENT = 0, MERGE_PASS = 1, MERGE_SHORTCUT = 2, MERGE_GE
 template <class FP>
 struct MergeDesc {
     Fe<FP> alpha, beta;       // x of the children's outputs (division roots)
-    Fe<FP> lz, lx, ly;        // line(-A, -B), unscaled   (l0 + l1 x + l2 y = lz + lx x + ly y)
-    Fe<FP> slz, slx, sly;     // same, times 1/T (folds the inverse-transform scaling into the product)
+    Fe<FP> lz, lx, ly;        // line(-A, -B)   (l0 + l1 x + l2 y = lz + lx x + ly y)
     uint32_t mode, pad[3];
 };
 
 template <class FP>
 __global__ void k_merge_desc(const Affine<FP>* __restrict__ child, size_t child_stride, const int* __restrict__ child_cnt,
-                             const Affine<FP>* __restrict__ parent, size_t parent_stride, int ntrees, Fe<FP> tinv,
+                             const Affine<FP>* __restrict__ parent, size_t parent_stride, int ntrees,
                              MergeDesc<FP>* __restrict__ desc, int* __restrict__ iso_deg /* optional: per tree, += 1 per generic merge */) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= parent_stride * ntrees) return;
@@ -640,7 +639,7 @@ __global__ void k_merge_desc(const Affine<FP>* __restrict__ child, size_t child_
     int c = child_cnt[tree];
     MergeDesc<FP> dsc;
     dsc.pad[0] = dsc.pad[1] = dsc.pad[2] = 0;
-    dsc.alpha = dsc.beta = dsc.lz = dsc.lx = dsc.ly = dsc.slz = dsc.slx = dsc.sly = Fe<FP>::zero();
+    dsc.alpha = dsc.beta = dsc.lz = dsc.lx = dsc.ly = Fe<FP>::zero();
     if ((long long)(2 * j) >= c) dsc.mode = MERGE_ABSENT;
     else if ((long long)(2 * j + 1) >= c) dsc.mode = MERGE_PASS;
     else {
@@ -651,7 +650,6 @@ __global__ void k_merge_desc(const Affine<FP>* __restrict__ child, size_t child_
             if (iso_deg) atomicAdd(iso_deg + tree, 1);
             dsc.alpha = a.x; dsc.beta = b.x;
             line_coeffs(aneg(a), aneg(b), ldg_aff(parent + g), dsc.lx, dsc.ly, dsc.lz);
-            dsc.slz = mul(dsc.lz, tinv); dsc.slx = mul(dsc.lx, tinv); dsc.sly = mul(dsc.ly, tinv);
         }
     }
     desc[g] = dsc;
@@ -669,18 +667,24 @@ constexpr int NTT_TILE_LOG = 10;
 constexpr int NTT_TILE = 1 << NTT_TILE_LOG;
 constexpr int NTT_THREADS = 256;
 
+// one polynomial family of a pass (blockIdx.y selects it: the a and the b polynomials of a level are transformed by ONE launch)
+template <class FP>
+struct NttSide {
+    Fe<FP>* data;            // workspace, n_transforms * T
+    const Fe<FP>* src;       // optional compact source (first pass)
+    Fe<FP>* dst;             // optional compact destination (last pass)
+    const Fe<FP>* sub_top;   // optional: sub_top[transform] is subtracted from every scattered output
+    size_t src_stride, dst_stride;
+    int src_len, dst_len;
+};
 template <class FP>
 struct NttPass {
-    Fe<FP>* data;            // workspace, n_transforms * T
-    const Fe<FP>* src;       // optional compact source (first forward pass)
-    Fe<FP>* dst;             // optional compact destination (last inverse pass)
+    NttSide<FP> side[2];
     const Fe<FP>* tw;        // tw[e] = w_T^e (or w_T^-e), e < T/2
     const Fe<FP>* twist;     // optional: element i of the gathered source is multiplied by twist[i] (coset transform)
-    const Fe<FP>* sub_top;   // optional: sub_top[transform] is subtracted from every scattered output
     const int* counts;       // transforms present per tree
     size_t total;            // n_transforms * T
-    size_t src_stride, dst_stride, dst_off;
-    int src_len, dst_len;
+    size_t dst_off;
     int node_max;            // transforms per tree (stride of the tree index)
     int t, s_hi, s_lo;
     int tw_t;                // log2 of the transform size the twiddle table `tw` belongs to (the contiguous pass uses the compact 2^k table)
@@ -739,6 +743,16 @@ k_ntt_pass(NttPass<FP> a) {
     const int lw = NTT_TILE_LOG - k;
     const size_t tile = blockIdx.x;
     const size_t Tmask = ((size_t)1 << a.t) - 1;
+    const NttSide<FP>& sd = a.side[blockIdx.y];
+    {   // Tiles whose transforms all belong to absent nodes (trees shorter than the longest one of the batch: ~15 % of the tiles of a
+        // 2^20-point witness) do no work at all.  A strided pass touches one transform per tile, the contiguous pass 2^(10-k)
+        // consecutive ones; a tile that straddles two trees is treated as present.
+        const size_t first = a.s_lo == 0 ? tile << NTT_TILE_LOG : (((tile << lw) >> a.s_lo) << (a.s_hi + 1));
+        const size_t last = a.s_lo == 0 ? first + NTT_TILE - 1 : first;
+        const uint32_t tr0 = (uint32_t)(first >> a.t), tr1 = (uint32_t)(last >> a.t);
+        const uint32_t tree0 = tr0 / (uint32_t)a.node_max, tree1 = tr1 / (uint32_t)a.node_max;
+        if (tree0 == tree1 && (int)(tr0 - tree0 * (uint32_t)a.node_max) >= a.counts[tree0]) return;
+    }
 
     size_t lin[4];
     bool live[4];
@@ -760,13 +774,13 @@ k_ntt_pass(NttPass<FP> a) {
             live[r] = node < a.counts[tree];
             if (live[r]) {
                 size_t i = lin[r] & Tmask;
-                if (a.src) {
-                    if ((int)i < a.src_len) {
-                        v = ldg(a.src + tr * a.src_stride + i);
+                if (sd.src) {
+                    if ((int)i < sd.src_len) {
+                        v = ldg(sd.src + tr * sd.src_stride + i);
                         if (a.twist) v = mul(v, ldg(a.twist + i));
                     }
                 }
-                else v = ldg(a.data + lin[r]);
+                else v = ldg(sd.data + lin[r]);
             }
         }
         ntt_sts(sm, (E << lw) | wl, v);
@@ -863,14 +877,14 @@ k_ntt_pass(NttPass<FP> a) {
         if (a.s_lo == 0) { E = q & ((1u << k) - 1); wl = q >> k; }
         else { wl = q & ((1u << lw) - 1); E = q >> lw; }
         Fe<FP> v = ntt_lds<FP>(sm, (E << lw) | wl);
-        if (a.dst) {
+        if (sd.dst) {
             size_t tr = lin[r] >> a.t, i = lin[r] & Tmask;
-            if ((int)i < a.dst_len) {
-                if (a.sub_top) v = sub(v, ldg(a.sub_top + tr));
-                stg(a.dst + tr * a.dst_stride + a.dst_off + i, v);
+            if ((int)i < sd.dst_len) {
+                if (sd.sub_top) v = sub(v, ldg(sd.sub_top + tr));
+                stg(sd.dst + tr * sd.dst_stride + a.dst_off + i, v);
             }
         } else {
-            stg(a.data + lin[r], v);
+            stg(sd.data + lin[r], v);
         }
     }
 }
@@ -1040,12 +1054,17 @@ __global__ void k_fixup(const MergeDesc<FP>* __restrict__ desc, size_t nmerges, 
     stg(top + m, q);
 }
 
-// twist[i] = w_{2T}^i * scale, i < T  (tw2 = table of the 2T-point transform): the odd-coset pre-multiplier that also
-// undoes the s-scaling of stored coefficients
+// Odd-coset pre-multipliers of every level in one table laid out like the twiddle table: for the merge that transforms children
+// of m = 2^l coefficients, twist[m + i] = w_{2m}^i * 2^-l, i < m (w_{2m}^i is tw_all[m + i]); the factor 2^-l undoes the scaling the
+// unscaled inverse transforms leave in the stored coefficients.
 template <class FP>
-__global__ void k_gen_twist(const Fe<FP>* __restrict__ tw2, size_t T, Fe<FP> scale, Fe<FP>* __restrict__ out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < T) stg(out + i, mul(ldg(tw2 + i), scale));
+__global__ void k_gen_twist_all(const Fe<FP>* __restrict__ tw_all, int tmax, Fe<FP>* __restrict__ out) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0 || idx >= ((size_t)1 << tmax)) return;
+    int l = 63 - __clzll((unsigned long long)idx);
+    Fe<FP> sc = Fe<FP>::one(), h = Fe<FP>::two_inv();
+    for (int i = 0; i < l; ++i) sc = mul(sc, h);
+    stg(out + idx, mul(ldg(tw_all + idx), sc));
 }
 
 // out[i] *= c (root rescale in raw mode)

@@ -197,6 +197,25 @@ def test_divisor_witness_vs_oracle(gpu_ctx, oracle, eagen, cname, n):
     assert e.value.status == eagen.E_SUM_NONZERO
 
 
+def test_divisor_witness_reference_test_shape_10000(gpu_ctx, oracle, eagen):
+    """randpoints_witness_test at the reference's own size (src/regular_functions_utils.rs:653-659): 10 000 copies of one Grumpkin
+    point plus minus their sum, and the same shape with 10 000 distinct points; raw and canonical form against the oracle"""
+    cv, ctx = pyref.Curve("grumpkin"), gpu_ctx("grumpkin")
+    pts, _ = gen(cv, 10000, 653)
+    a = pts[0]
+    acc = None
+    for q in pts:
+        acc = cv.add(acc, q)
+    for v in ([a] * 10000 + [cv.neg(cv.mul(10000, a))], pts + [cv.neg(acc)]):
+        P = oracle.pack_points(v, cv.p)
+        ro = oracle.divisor_witness(cv.id, P)
+        fr = ctx.compute_divisor_witness(P, eagen.RAW_TREE)
+        assert same(fr.a, trim(ro.a[0])) and same(fr.b, trim(ro.b[0]))
+        fc = ctx.compute_divisor_witness(P, eagen.CANONICAL)
+        assert same(fc.a, ro.ca[0]) and same(fc.b, ro.cb[0])
+        assert not ctx.eval_function(fc, P[:: 97]).any()
+
+
 def test_divisor_witness_degenerate_geometry(gpu_ctx, oracle, eagen):
     """repeated points (the reference's tests use ONE point 10 000 times), P/-P pairs, identities"""
     cv, ctx = pyref.Curve("grumpkin"), gpu_ctx("grumpkin")
@@ -256,10 +275,10 @@ def test_lhs_repeated_point_reference_test_shape(gpu_ctx, oracle, eagen):
     assert oracle.unpack_affine(res.carry, cv.p)[0] == cv.mul(sc[0] * n % cv.q, pts[0])
     ro = oracle.lhs_witness(cv.id, S, P, 5, with_functions=False)
     assert (res.digits == ro.digits).all() and (res.carries == ro.carries).all()
-    # compare three of the 56 functions with the oracle's tree on the same tmp list
+    # compare ALL 56 functions with the oracle's tree on the same tmp list
     carries = oracle.unpack_affine(ro.carries, cv.p)
     mult = [cv.mul(k, pts[0]) for k in range(1, 5)]
-    for i in (0, 20, 55):
+    for i in range(ro.d):
         prev = carries[i - 1] if i else None
         dg = int(ro.digits[0][i])
         tmp = ([cv.neg(prev)] * 5 if prev is not None else []) + ([mult[dg - 1]] * n if dg else []) + [cv.neg(carries[i])]

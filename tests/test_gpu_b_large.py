@@ -1,6 +1,10 @@
-"""GPU tests at BASELINE.json sizes (pytest -m gpu): 2^16 against the oracle on sampled trees, 2^20 through
-size-independent properties (carry == independent MSM on the oracle side, functions vanish on their points,
-degrees, canonical = scaled raw)."""
+"""GPU tests at BASELINE.json sizes (pytest -m gpu): config 2 (2^16) with ALL functions against the oracle, config 3 (2^20)
+against the committed SHA-256 of the oracle's full-size run (every digit, carry and coefficient) and through
+size-independent properties (carry == independent MSM on the oracle side, functions vanish on their points, degrees,
+the norm identity)."""
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -42,6 +46,69 @@ def neg_affine(row, p, oracle):
 
 
 @pytest.mark.parametrize("cname,log_n", [("pallas", 16), ("vesta", 14)])
+def test_config2_all_functions_vs_oracle(gpu_ctx, oracle, eagen, cname, log_n):
+    """BASELINE config 2: digits, carries and ALL d canonical (a, b) bit-exact against the oracle's own
+    full compute_lhs_witness on the same inputs (about 40 s of oracle at 2^16 on the box's host cores)."""
+    cv, ctx = pyref.Curve(cname), gpu_ctx(cname)
+    n, base = 1 << log_n, 5
+    oracle.set_threads(os.cpu_count() or 1)
+    S, P = ctx.synth_inputs(0xEA6E0001, n)
+    res = ctx.compute_lhs_witness(S, P, base, eagen.CANONICAL | eagen.KEEP_DIGITS)
+    ro = oracle.lhs_witness(cv.id, S, P, base)
+    assert (res.digits == ro.digits).all()
+    assert (res.carries == ro.carries).all() and (res.carry == ro.carry).all()
+    assert res.num_functions == ro.d == len(ro.ca)
+    for k in range(ro.d):
+        f = res.function(k)
+        assert f.a.shape == ro.ca[k].shape and (f.a == ro.ca[k]).all(), k
+        assert f.b.shape == ro.cb[k].shape and (f.b == ro.cb[k]).all(), k
+    res.free()
+
+
+@pytest.mark.parametrize("cname", ["pallas", "vesta", "grumpkin"])
+def test_synthetic_inputs_match_the_oracle_restatement(gpu_ctx, oracle, cname):
+    """the golden hashes below were computed from oracle_synth_inputs: the device generator must describe the same scalars and the
+    same points (it emits Jacobian triples with non-trivial z, the oracle z = 1; compare the affine points)"""
+    cv, ctx = pyref.Curve(cname), gpu_ctx(cname)
+    for seed, n in ((0xEA6E0002, 1031), (7, 64)):
+        S, P = ctx.synth_inputs(seed, n)
+        So, Po = oracle.synth_inputs(cv.id, seed, n)
+        assert (S == So).all()
+        aff = ctx.precompute_multiplicities(P, 2)[:, 0, :]          # 1 * P_j, affine
+        assert (aff == Po[:, :8]).all()
+
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("fname", sorted(f for f in os.listdir(GOLDEN) if f.startswith("lhs_") and f.endswith("_hashes.json")))
+def test_full_size_hashes(gpu_ctx, eagen, fname):
+    """BASELINE config 3 (and any other committed full-size run): every digit, every carry and every coefficient of all d
+    canonical functions against the SHA-256 record of the oracle's own full-size run (tools/golden_full_size.py; 2^20 Pallas
+    points took the oracle 30 min on 8 cores).  This pins every kernel change at the metric's size."""
+    from hashes import witness_hashes
+    with open(os.path.join(GOLDEN, fname)) as f:
+        gold = json.load(f)
+    ctx = gpu_ctx(gold["curve"])
+    n = 1 << gold["log_n"]
+    S, P = ctx.synth_inputs(int(gold["seed"], 0), n)
+    res = ctx.compute_lhs_witness(S, P, gold["base"], eagen.CANONICAL | eagen.KEEP_DIGITS)
+    assert res.d == gold["d"] == res.num_functions
+    fa, fb = [], []
+    for k in range(res.d):
+        f = res.function(k)
+        fa.append(f.a)
+        fb.append(f.b)
+    rec = witness_hashes(res.digits, res.carries, fa, fb)
+    res.free()
+    assert rec["digits"] == gold["digits"]
+    assert rec["carries"] == gold["carries"]
+    for k, (g, h) in enumerate(zip(gold["functions"], rec["functions"])):
+        assert (g["la"], g["lb"]) == (h["la"], h["lb"]), k
+        assert g["sha256"] == h["sha256"], k
+
+
+@pytest.mark.parametrize("cname,log_n", [("grumpkin", 13)])
 def test_config2_sampled_trees_vs_oracle(gpu_ctx, oracle, eagen, cname, log_n):
     cv, ctx = pyref.Curve(cname), gpu_ctx(cname)
     n, base = 1 << log_n, 5

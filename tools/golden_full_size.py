@@ -11,7 +11,6 @@ The -m gpu test tests/test_gpu_b_large.py::test_full_size_hashes compares the CU
 pins every later kernel change at full size.  Test infrastructure: nothing here is imported by the product.
 """
 import argparse
-import hashlib
 import json
 import os
 import sys
@@ -22,20 +21,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 import oracle_lib  # noqa: E402
+from hashes import witness_hashes  # noqa: E402
 
 CURVES = {"pallas": 0, "vesta": 1, "grumpkin": 2}
-
-
-def witness_hashes(digits, carries, fa, fb):
-    """the hash record both sides compute: digits (n,d) u8 MSD first, carries (d,8) u64, canonical a_k / b_k as (len,4) u64"""
-    rec = {"digits": hashlib.sha256(np.ascontiguousarray(digits).tobytes()).hexdigest(),
-           "carries": hashlib.sha256(np.ascontiguousarray(carries).tobytes()).hexdigest(), "functions": []}
-    for a, b in zip(fa, fb):
-        h = hashlib.sha256()
-        h.update(np.ascontiguousarray(a).tobytes())
-        h.update(np.ascontiguousarray(b).tobytes())
-        rec["functions"].append({"la": int(len(a)), "lb": int(len(b)), "sha256": h.hexdigest()})
-    return rec
 
 
 def main():
