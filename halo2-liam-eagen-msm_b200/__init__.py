@@ -50,9 +50,38 @@ ABI_SYMBOLS = [
     "eagen_dev_negbase", "eagen_dev_ntt", "eagen_lhs_witness_stream", "eagen_lhs_witness_stream_layout",
     "eagen_table_entry_by_id", "eagen_msm", "eagen_prepare_scalar_witness", "eagen_divisor_witness_naive",
     "eagen_circuit_sizes", "eagen_result_copy_padded", "eagen_result_eval", "eagen_to_curve_x", "eagen_y_from_x", "eagen_slope",
+    "eagen_ctx_set_stream_split", "eagen_comm_unique_id", "eagen_comm_init", "eagen_comm_init_all", "eagen_comm_destroy",
+    "eagen_comm_size", "eagen_comm_rank", "eagen_position_range", "eagen_lhs_witness_sharded_layout", "eagen_lhs_witness_sharded",
+    "eagen_dev_lhs_witness_sharded", "eagen_result_first_function",
 ]
+COMM_ID_BYTES = 128
 SELFTEST_SYMBOLS = ["eagen_selftest_field", "eagen_selftest_curve", "eagen_selftest_negbase_params", "eagen_selftest_negbase_digits",
                     "eagen_selftest_ntt_plan"]
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it and ships it to the other ranks through any side channel)"""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = lib().eagen_comm_unique_id(buf)
+    if rc != 0:
+        raise EagenError(rc, lib().eagen_last_error(None).decode())
+    return buf.raw
+
+
+def comm_init_all(ctxs):
+    """single-process multi-GPU: one NCCL communicator over the contexts' devices (the sharded call then needs one host thread per context)"""
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    rc = lib().eagen_comm_init_all(arr, len(ctxs))
+    if rc != 0:
+        raise EagenError(rc, lib().eagen_last_error(ctxs[0]._h).decode())
+
+
+def position_range(rank, nranks, d):
+    b, e = C.c_uint32(), C.c_uint32()
+    rc = lib().eagen_position_range(rank, nranks, d, C.byref(b), C.byref(e))
+    if rc != 0:
+        raise EagenError(rc, "eagen_position_range: bad arguments")
+    return b.value, e.value
 
 
 class EagenError(RuntimeError):
@@ -135,6 +164,21 @@ def lib():
         L.eagen_to_curve_x.argtypes = [C.c_int, U64P, U64P]
         L.eagen_y_from_x.argtypes = [C.c_int, U64P, U64P, C.POINTER(C.c_int)]
         L.eagen_slope.argtypes = [C.c_int, U64P, U64P]
+        L.eagen_ctx_set_stream_split.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.c_int]
+        L.eagen_comm_unique_id.argtypes = [C.c_void_p]
+        L.eagen_comm_init.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.eagen_comm_init_all.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.eagen_comm_destroy.argtypes = [C.c_void_p]
+        L.eagen_comm_size.argtypes = [C.c_void_p]
+        L.eagen_comm_rank.argtypes = [C.c_void_p]
+        L.eagen_position_range.argtypes = [C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.eagen_lhs_witness_sharded_layout.argtypes = [C.c_int, C.c_size_t, C.c_uint8, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                                       C.POINTER(C.c_size_t)]
+        L.eagen_lhs_witness_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8, C.c_uint32, C.c_void_p, C.c_size_t,
+                                                C.POINTER(C.c_void_p)]
+        L.eagen_dev_lhs_witness_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint8, C.c_uint32, C.POINTER(C.c_void_p)]
+        L.eagen_result_first_function.restype = C.c_size_t
+        L.eagen_result_first_function.argtypes = [C.c_void_p]
         L.eagen_selftest_field.argtypes = [C.c_int, C.c_int, U64P, U64P, U64P]
         L.eagen_selftest_curve.argtypes = [C.c_int, C.c_int, U64P, U64P, C.c_uint32, U64P]
         L.eagen_selftest_negbase_params.argtypes = [C.c_int, C.c_uint8, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
@@ -243,6 +287,7 @@ class WitnessResult:
         self.d = L.eagen_result_num_digits(handle)
         self.num_functions = L.eagen_result_num_functions(handle)
         self.device_ms = L.eagen_result_device_ms(handle)
+        self.first_function = L.eagen_result_first_function(handle)   # digit position of slot 0 (non-zero for a rank's share)
 
     def poly(self, k, which):
         L = lib()
@@ -352,6 +397,47 @@ class Context:
         v = C.c_double()
         self._chk(lib().eagen_microbench(self._h, which, C.byref(v)))
         return v.value
+
+    # ---- multi-GPU (one context per rank; see eagen_lhs_witness_sharded in include/eagen_msm.h) ----------------------
+    def comm_init(self, nranks, rank, unique_id):
+        """join the NCCL communicator described by the 128-byte id every rank received from rank 0 (comm_unique_id())"""
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        self._chk(lib().eagen_comm_init(self._h, nranks, rank, buf))
+
+    def comm_destroy(self):
+        self._chk(lib().eagen_comm_destroy(self._h))
+
+    def comm_size(self):
+        return lib().eagen_comm_size(self._h)
+
+    def comm_rank(self):
+        return lib().eagen_comm_rank(self._h)
+
+    def set_stream_split(self, percents):
+        arr = (C.c_uint32 * len(percents))(*percents)
+        self._chk(lib().eagen_ctx_set_stream_split(self._h, arr, len(percents)))
+
+    def sharded_layout(self, n_total, base, rank, nranks):
+        a, b, t = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        self._chk(lib().eagen_lhs_witness_sharded_layout(self.curve, n_total, C.c_uint8(base), rank, nranks, C.byref(a), C.byref(b), C.byref(t)))
+        return a.value, b.value, t.value
+
+    def lhs_witness_sharded_ptr(self, scalars_ptr, pts_ptr, n_local, base, flags=CANONICAL, device=False, out_ptr=None, out_bytes=0):
+        """this rank's share of compute_lhs_witness over all ranks' points (raw pointers: host, or device with device=True);
+        out_ptr: host buffer the rank's functions are streamed into (host-input form only)"""
+        h = C.c_void_p()
+        if device:
+            self._chk(lib().eagen_dev_lhs_witness_sharded(self._h, C.c_void_p(scalars_ptr), C.c_void_p(pts_ptr), n_local, C.c_uint8(base), flags, C.byref(h)))
+        else:
+            self._chk(lib().eagen_lhs_witness_sharded(self._h, C.c_void_p(scalars_ptr), C.c_void_p(pts_ptr), n_local, C.c_uint8(base), flags,
+                                                      C.c_void_p(out_ptr) if out_ptr else None, out_bytes, C.byref(h)))
+        return WitnessResult(self, h, n_local * max(self.comm_size(), 1))
+
+    def lhs_witness_sharded(self, scalars, pts, base, flags=CANONICAL):
+        s, p = _arr(scalars, 4), _arr(pts, 12)
+        if len(s) != len(p):
+            raise EagenError(E_LEN, "incompatible amount of coefficients")
+        return self.lhs_witness_sharded_ptr(s.ctypes.data, p.ctypes.data, len(p), base, flags)
 
     def set_profiling(self, on=True):
         self._chk(lib().eagen_set_profiling(self._h, int(on)))

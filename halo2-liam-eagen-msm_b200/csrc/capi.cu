@@ -8,6 +8,8 @@ struct eagen_ctx {
     int curve;
     IEngine* eng;
     std::string err;
+    bool comm_from_init_all = false;   // communicator created by eagen_comm_init_all: destroyed by eagen_comm_destroy / ctx_destroy
+    void* raw_comm = nullptr;
 };
 struct eagen_result {
     ResultImpl* r;
@@ -46,9 +48,15 @@ uint32_t digits_of_curve(int curve, uint8_t base) {
 }
 template <class FP> void precomp(int which, uint64_t e, uint64_t* out) {
     Fe<FP> r;
-    if (which == 0) r = pow2k(Fe<FP>::root_of_unity(), (unsigned)std::min<uint64_t>(e, 300));
-    else if (which == 1) r = pow2k(Fe<FP>::root_of_unity_inv(), (unsigned)std::min<uint64_t>(e, 300));
-    else { r = Fe<FP>::one(); for (uint64_t i = 0; i < e; ++i) r = mul(r, Fe<FP>::two_inv()); }
+    if (which == 0 || which == 1) {
+        // omega_pow(k) = ROOT_OF_UNITY^(2^k): the identity from k = S on, so larger exponents need no more squarings
+        unsigned k = (unsigned)std::min<uint64_t>(e, FP::S);
+        r = pow2k(which == 0 ? Fe<FP>::root_of_unity() : Fe<FP>::root_of_unity_inv(), k);
+    } else {   // (1/2)^e by square-and-multiply (a 64-bit exponent must not become a 2^64-step loop)
+        r = Fe<FP>::one();
+        Fe<FP> b = Fe<FP>::two_inv();
+        for (uint64_t x = e; x; x >>= 1) { if (x & 1) r = mul(r, b); b = sqr(b); }
+    }
     std::memcpy(out, r.v, 32);
 }
 // table_entry_by_id restated on the host with the kernels' field code (reference: src/negbase_utils.rs:58-77)
@@ -174,7 +182,8 @@ int eagen_ctx_create(int curve, int device, eagen_ctx** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); g_global_err = "no CUDA device visible"; return EAGEN_E_NO_DEVICE; }
     if (device < 0 || device >= ndev) { g_global_err = "device index out of range"; return EAGEN_E_ARG; }
-    eagen_ctx* c = new eagen_ctx{curve, nullptr, ""};
+    eagen_ctx* c = new eagen_ctx();
+    c->curve = curve; c->eng = nullptr;
     int rc = guarded(nullptr, [&] {
         switch (curve) {
             case EAGEN_CURVE_PALLAS: c->eng = make_engine_pallas(device); break;
@@ -190,6 +199,7 @@ int eagen_ctx_create(int curve, int device, eagen_ctx** out) {
 
 void eagen_ctx_destroy(eagen_ctx* ctx) {
     if (!ctx) return;
+    eagen_comm_destroy(ctx);
     delete ctx->eng;
     delete ctx;
 }
@@ -341,6 +351,86 @@ int eagen_dev_trees(eagen_ctx* ctx, const void* d_planes, const void* d_table, c
         *out = new eagen_result{ctx->eng->trees_dev(d_planes, d_table, d_carries, n, base, pos_begin, pos_end, flags)};
     });
 }
+
+// ---- multi-GPU behind the boundary ---------------------------------------------------
+int eagen_comm_unique_id(void* id_out) {
+    return guarded(nullptr, [&] {
+        need(id_out != nullptr, "eagen_comm_unique_id: null output");
+        NcclApi& nc = NcclApi::get();
+        if (!nc.ok) throw StatusError{EAGEN_E_NCCL, nc.load_error};
+        ncclUniqueId id;
+        ncclResult_t r = nc.GetUniqueId(&id);
+        if (r != ncclSuccess) throw StatusError{EAGEN_E_NCCL, std::string("ncclGetUniqueId: ") + nc.GetErrorString(r)};
+        static_assert(sizeof(ncclUniqueId) == EAGEN_COMM_ID_BYTES, "unique id size");
+        std::memcpy(id_out, &id, sizeof id);
+    });
+}
+int eagen_comm_init(eagen_ctx* ctx, int nranks, int rank, const void* unique_id) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] { ctx->eng->comm_init_rank(nranks, rank, unique_id); });
+}
+int eagen_comm_init_all(eagen_ctx** ctxs, int n) {
+    if (!ctxs || n < 1) return EAGEN_E_ARG;
+    for (int i = 0; i < n; ++i) if (!ctxs[i]) return EAGEN_E_ARG;
+    return guarded(ctxs[0], [&] {
+        NcclApi& nc = NcclApi::get();
+        if (!nc.ok) throw StatusError{EAGEN_E_NCCL, nc.load_error};
+        std::vector<int> devs(n);
+        for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->eng->device();
+        std::vector<ncclComm_t> comms(n);
+        ncclResult_t r = nc.CommInitAll(comms.data(), n, devs.data());
+        if (r != ncclSuccess) throw StatusError{EAGEN_E_NCCL, std::string("ncclCommInitAll: ") + nc.GetErrorString(r)};
+        for (int i = 0; i < n; ++i) { ctxs[i]->eng->comm_attach(comms[i], n, i); ctxs[i]->comm_from_init_all = true; ctxs[i]->raw_comm = comms[i]; }
+    });
+}
+int eagen_comm_destroy(eagen_ctx* ctx) {
+    if (!ctx) return EAGEN_E_ARG;
+    return guarded(ctx, [&] {
+        ctx->eng->comm_destroy();
+        if (ctx->comm_from_init_all && ctx->raw_comm) { NcclApi::get().CommDestroy((ncclComm_t)ctx->raw_comm); }
+        ctx->comm_from_init_all = false; ctx->raw_comm = nullptr;
+    });
+}
+int eagen_comm_size(const eagen_ctx* ctx) { return ctx ? ctx->eng->comm_size() : 0; }
+int eagen_comm_rank(const eagen_ctx* ctx) { return ctx ? ctx->eng->comm_rank() : -1; }
+int eagen_position_range(int rank, int nranks, uint32_t d, uint32_t* begin, uint32_t* end) {
+    if (!begin || !end || nranks < 1 || rank < 0 || rank >= nranks) return EAGEN_E_ARG;
+    position_range(rank, nranks, d, begin, end);
+    return EAGEN_OK;
+}
+int eagen_lhs_witness_sharded(eagen_ctx* ctx, const uint64_t* scalars_local, const uint64_t* pts_local, size_t n_local, uint8_t base, uint32_t flags,
+                              void* out, size_t out_bytes, eagen_result** res) {
+    if (!ctx || !res) return EAGEN_E_ARG;
+    *res = nullptr;
+    return guarded(ctx, [&] {
+        need(base >= 2 && (n_local == 0 || (scalars_local && pts_local)), "eagen_lhs_witness_sharded: bad arguments");
+        *res = new eagen_result{ctx->eng->lhs_sharded(scalars_local, pts_local, false, n_local, base, flags, out, out_bytes)};
+    });
+}
+int eagen_dev_lhs_witness_sharded(eagen_ctx* ctx, const void* d_scalars_local, const void* d_pts_local, size_t n_local, uint8_t base, uint32_t flags,
+                                  eagen_result** res) {
+    if (!ctx || !res) return EAGEN_E_ARG;
+    *res = nullptr;
+    return guarded(ctx, [&] {
+        need(base >= 2 && (n_local == 0 || (d_scalars_local && d_pts_local)), "eagen_dev_lhs_witness_sharded: bad arguments");
+        *res = new eagen_result{ctx->eng->lhs_sharded(d_scalars_local, d_pts_local, true, n_local, base, flags, nullptr, 0)};
+    });
+}
+int eagen_lhs_witness_sharded_layout(int curve, size_t n_total, uint8_t base, int rank, int nranks, size_t* a_stride, size_t* b_stride, size_t* total_bytes) {
+    return guarded(nullptr, [&] {
+        need(a_stride && b_stride && base >= 2 && nranks >= 1 && rank >= 0 && rank < nranks, "eagen_lhs_witness_sharded_layout: bad arguments");
+        stream_slot_elems(n_total, base, a_stride, b_stride);
+        uint32_t b0, b1;
+        position_range(rank, nranks, digits_of_curve(curve, base), &b0, &b1);
+        if (total_bytes) *total_bytes = (size_t)(b1 - b0) * (*a_stride + *b_stride) * 32;
+    });
+}
+int eagen_ctx_set_stream_split(eagen_ctx* ctx, const uint32_t* percent, int n) {
+    if (!ctx || n < 0 || (n > 0 && !percent)) return EAGEN_E_ARG;
+    ctx->eng->set_stream_split(percent, n);
+    return EAGEN_OK;
+}
+size_t eagen_result_first_function(const eagen_result* r) { return r ? r->r->k0 : 0; }
 
 int eagen_synth_inputs(eagen_ctx* ctx, uint64_t seed, size_t n, uint64_t* scalars, uint64_t* pts) {
     if (!ctx) return EAGEN_E_ARG;

@@ -17,6 +17,7 @@
 #include <vector>
 #include "../../include/eagen_msm.h"
 #include "kernels.cuh"
+#include "comm.cuh"
 
 namespace eagen {
 
@@ -36,6 +37,20 @@ struct StatusError {
     int code;
     std::string msg;
 };
+
+#define EAGEN_NCCL(call)                                                                                        \
+    do {                                                                                                        \
+        ncclResult_t r_ = (call);                                                                               \
+        if (r_ != ncclSuccess)                                                                                  \
+            throw StatusError{EAGEN_E_NCCL, std::string(#call) + ": " + (NcclApi::get().GetErrorString ? NcclApi::get().GetErrorString(r_) : "NCCL error")}; \
+    } while (0)
+
+// contiguous, balanced split of the d digit positions over the ranks (56 = 8 x 7 at base 5)
+inline void position_range(int rank, int nranks, uint32_t d, uint32_t* begin, uint32_t* end) {
+    uint32_t q = d / (uint32_t)nranks, r = d % (uint32_t)nranks;
+    *begin = (uint32_t)rank * q + std::min<uint32_t>((uint32_t)rank, r);
+    *end = *begin + q + ((uint32_t)rank < r ? 1u : 0u);
+}
 
 // grow-only device buffer
 struct DevBuf {
@@ -120,6 +135,7 @@ struct ResultImpl {
     uint32_t d = 0;
     size_t n = 0;
     size_t nf = 0;                       // functions held
+    size_t k0 = 0;                       // digit position (function index of the whole witness) of slot 0: non-zero for a rank's share
     size_t a_stride = 0, b_stride = 0;   // elements
     DevBuf A, B;                         // nf x stride field elements
     std::vector<int> la, lb;             // trimmed lengths
@@ -169,6 +185,14 @@ struct IEngine {
     virtual void naive_host(const uint64_t* pts, size_t n, uint64_t* pos, size_t* n_pos, uint64_t* neg, size_t* n_neg) = 0;
     virtual void result_eval_host(ResultImpl* r, const uint64_t* pts, size_t m, uint64_t* out) = 0;
     virtual double microbench(int which) = 0;
+    virtual void comm_attach(void* nccl_comm, int nranks, int rank) = 0;
+    virtual void comm_init_rank(int nranks, int rank, const void* unique_id) = 0;
+    virtual void comm_destroy() = 0;
+    virtual int comm_size() const = 0;
+    virtual int comm_rank() const = 0;
+    virtual ResultImpl* lhs_sharded(const void* scalars, const void* pts, bool device_inputs, size_t n_local, uint8_t base, uint32_t flags,
+                                    void* out, size_t out_bytes) = 0;
+    virtual void set_stream_split(const uint32_t* pct, int n) = 0;
     virtual void set_profiling(int mode) = 0;
     virtual std::string profile_json() = 0;
     virtual void profile_reset() = 0;
@@ -310,6 +334,8 @@ public:
     ~Engine() override {
         cudaSetDevice(dev_);
         cudaStreamSynchronize(st_);
+        if (comm_ && comm_owned_ && NcclApi::get().ok) NcclApi::get().CommDestroy(comm_);
+        if (nst_) cudaStreamDestroy(nst_);
         cudaFree(d_err_); cudaFree(d_one_);
         cudaEventDestroy(ev0_); cudaEventDestroy(ev1_);
         for (cudaEvent_t e : sync_events_) cudaEventDestroy(e);
@@ -526,6 +552,128 @@ public:
         sync_check();
         float ms = 0; EAGEN_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
         return ms;
+    }
+
+    // ------------------------------------------------------------------------------------------------
+    // multi-GPU: one context per rank / device, NCCL communicator owned by the context
+    // ------------------------------------------------------------------------------------------------
+    void comm_attach(void* nccl_comm, int nranks, int rank) override {   // communicator created by the caller (ncclCommInitAll): not destroyed here
+        comm_destroy();
+        comm_ = (ncclComm_t)nccl_comm; nranks_ = nranks; rank_ = rank; comm_owned_ = false;
+        ensure_comm_stream();
+    }
+    void comm_init_rank(int nranks, int rank, const void* unique_id) override {
+        use();
+        NcclApi& nc = NcclApi::get();
+        if (!nc.ok) throw StatusError{EAGEN_E_NCCL, nc.load_error};
+        if (nranks < 1 || rank < 0 || rank >= nranks || !unique_id) throw StatusError{EAGEN_E_ARG, "eagen_comm_init: bad rank / size / id"};
+        comm_destroy();
+        ncclUniqueId id;
+        std::memcpy(&id, unique_id, sizeof id);
+        EAGEN_NCCL(nc.CommInitRank(&comm_, nranks, id, rank));
+        nranks_ = nranks; rank_ = rank; comm_owned_ = true;
+        ensure_comm_stream();
+    }
+    void comm_destroy() override {
+        if (comm_ && comm_owned_) { use(); cudaStreamSynchronize(st_); if (nst_) cudaStreamSynchronize(nst_); NcclApi::get().CommDestroy(comm_); }
+        comm_ = nullptr; nranks_ = 1; rank_ = 0; comm_owned_ = false;
+    }
+    int comm_size() const override { return nranks_; }
+    int comm_rank() const override { return rank_; }
+    void set_stream_split(const uint32_t* pct, int n) override {
+        stream_split_.clear();
+        for (int i = 0; i < n; ++i) if (pct[i] > 0) stream_split_.push_back(pct[i]);
+        if (stream_split_.empty()) { stream_split_.push_back(70); stream_split_.push_back(30); }
+    }
+
+    // compute_lhs_witness over the point ranges of ALL ranks; this rank passes its own n_local scalars / points (every rank the same
+    // n_local) and receives the functions of its share of the digit positions (position_range).  Stages:
+    //   K1-K3 on the local range  ->  all-gather of the d x 96-byte partial digit sums, the digit planes (one grouped all-gather,
+    //   landing position-major over the global point range) and the multiples table (the one real exchange: N x (b-1) x 64 B), all on
+    //   the communication stream  ->  carry chain (replicated; overlaps the plane / table gathers)  ->  this rank's trees.
+    // out != nullptr: host buffer the functions are streamed into (layout of eagen_lhs_witness_stream over the LOCAL slots).
+    ResultImpl* lhs_sharded(const void* scalars, const void* pts, bool device_inputs, size_t n_local, uint8_t base, uint32_t flags,
+                            void* out, size_t out_bytes) override {
+        use();
+        if (!comm_) throw StatusError{EAGEN_E_NCCL, "eagen_lhs_witness_sharded: no communicator (call eagen_comm_init first)"};
+        NcclApi& nc = NcclApi::get();
+        NegbaseParams prm = make_negbase_params<FS>(base);
+        const uint32_t d = prm.d;
+        const size_t W = (size_t)nranks_, n_total = n_local * W, nn = std::max<size_t>(n_local, 1);
+        uint32_t pos0, pos1;
+        position_range(rank_, nranks_, d, &pos0, &pos1);
+        StreamOut so;
+        if (out) {
+            so.out = (uint8_t*)out;
+            stream_slot_elems(n_total, base, &so.a_stride, &so.b_stride);
+            if (out_bytes < (size_t)(pos1 - pos0) * (so.a_stride + so.b_stride) * 32) throw StatusError{EAGEN_E_LEN, "streamed output buffer too small"};
+        }
+        const Fe<FS>* ds = (const Fe<FS>*)scalars;
+        const F* dp = (const F*)pts;
+        if (!device_inputs) {
+            Fe<FS>* hs = (Fe<FS>*)in_scalars_.ensure(nn * 32);
+            F* hp = (F*)in_points_.ensure(nn * 96);
+            if (n_local) {
+                EAGEN_CUDA(cudaMemcpyAsync(hs, scalars, n_local * 32, cudaMemcpyHostToDevice, st_));
+                EAGEN_CUDA(cudaMemcpyAsync(hp, pts, n_local * 96, cudaMemcpyHostToDevice, st_));
+            }
+            ds = hs; dp = hp;
+        }
+        EAGEN_CUDA(cudaEventRecord(ev0_, st_));
+        uint8_t* pl_local = (uint8_t*)sh_planes_.ensure(nn * d);
+        Aff* tab_local = (Aff*)sh_table_.ensure(nn * (size_t)(base - 1) * 64);
+        // [0, d): this rank's partial sums; [d, d + W*d): all ranks'; the 8-byte slots after them carry n_local of every rank
+        Prj* sums = (Prj*)sums_.ensure((size_t)(d + W * d) * sizeof(Prj) + (W + 1) * sizeof(unsigned long long));
+        Prj* all_sums = sums + d;
+        unsigned long long* nl = (unsigned long long*)(all_sums + W * d);   // nl[0]: mine, nl[1..W]: gathered
+        uint8_t* planes = (uint8_t*)planes_.ensure(std::max<size_t>(n_total, 1) * d);
+        Aff* tab = (Aff*)table_.ensure(std::max<size_t>(n_total, 1) * (size_t)(base - 1) * 64);
+        Aff* carries = (Aff*)carries_.ensure((size_t)d * sizeof(Aff));
+        std::unique_ptr<ResultImpl> res(new ResultImpl());
+        res->device = dev_; res->pool = pool_; res->d = d; res->n = n_total; res->k0 = d - pos1;
+        {
+            unsigned long long* stage = (unsigned long long*)ring_.take(sizeof(unsigned long long));
+            *stage = (unsigned long long)n_local;
+            EAGEN_CUDA(cudaMemcpyAsync(nl, stage, sizeof(unsigned long long), cudaMemcpyHostToDevice, st_));
+        }
+        run_shard_sums(ds, dp, n_local, prm, pl_local, nullptr, tab_local, sums);
+        // ---- the exchange, on the communication stream
+        EAGEN_CUDA(cudaEventRecord(sync_event(60), st_));
+        EAGEN_CUDA(cudaStreamWaitEvent(nst_, sync_event(60), 0));
+        unsigned long long* hnl = (unsigned long long*)ring_.take((W + 1) * sizeof(unsigned long long));
+        EAGEN_NCCL(nc.AllGather(nl, nl + 1, sizeof(unsigned long long), ncclUint8, comm_, nst_));
+        EAGEN_CUDA(cudaMemcpyAsync(hnl, nl, (W + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, nst_));
+        EAGEN_NCCL(nc.AllGather(sums, all_sums, (size_t)d * sizeof(Prj), ncclUint8, comm_, nst_));
+        EAGEN_CUDA(cudaEventRecord(sync_event(61), nst_));
+        if (n_local) {
+            // one all-gather per digit position, grouped into a single NCCL launch: row `pos` of every rank lands at its place in the
+            // position-major planes over the global point range (no transpose pass afterwards)
+            EAGEN_NCCL(nc.GroupStart());
+            for (uint32_t pos = 0; pos < d; ++pos)
+                EAGEN_NCCL(nc.AllGather(pl_local + (size_t)pos * n_local, planes + (size_t)pos * n_total, n_local, ncclUint8, comm_, nst_));
+            EAGEN_NCCL(nc.GroupEnd());
+            EAGEN_NCCL(nc.AllGather(tab_local, tab, n_local * (size_t)(base - 1) * 64, ncclUint8, comm_, nst_));
+        }
+        EAGEN_CUDA(cudaEventRecord(sync_event(62), nst_));
+        // ---- replicated carry chain while the planes / table are still in flight
+        EAGEN_CUDA(cudaStreamWaitEvent(st_, sync_event(61), 0));
+        run_carry_chain(all_sums, nranks_, d, base, carries);
+        res->carries.assign((size_t)d * 8, 0);
+        uint64_t* hcar = (uint64_t*)ring_.take((size_t)d * 64);
+        EAGEN_CUDA(cudaMemcpyAsync(hcar, carries, (size_t)d * 64, cudaMemcpyDeviceToHost, st_));
+        EAGEN_CUDA(cudaStreamWaitEvent(st_, sync_event(62), 0));
+        EAGEN_CUDA(cudaStreamSynchronize(nst_));   // n_local of every rank is on the host now
+        for (size_t r = 0; r < W; ++r)
+            if (hnl[1 + r] != (unsigned long long)n_local)
+                throw StatusError{EAGEN_E_LEN, "eagen_lhs_witness_sharded: every rank must pass the same number of points (pad with zero scalars)"};
+        if (!(flags & EAGEN_NO_FUNCTIONS)) run_position_trees(planes, tab, carries, n_total, base, d, pos0, pos1, flags, res.get(), out ? &so : nullptr);
+        EAGEN_CUDA(cudaEventRecord(ev1_, st_));
+        sync_check();
+        std::memcpy(res->carries.data(), hcar, (size_t)d * 64);
+        std::memcpy(res->carry, &res->carries[(size_t)(d - 1) * 8], 64);
+        float ms = 0; EAGEN_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+        res->device_ms = ms;
+        return res.release();
     }
 
     // which = 0: 32-bit IMAD per second; which = 1: base-field Montgomery products per second (register-resident chains)
@@ -903,6 +1051,13 @@ private:
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     int* d_err_ = nullptr;
     int last_tree_err_ = 0;
+    ncclComm_t comm_ = nullptr;                  // multi-GPU: this rank's communicator (null: single GPU)
+    int nranks_ = 1, rank_ = 0;
+    bool comm_owned_ = false;
+    cudaStream_t nst_ = nullptr;                 // communication stream (collectives overlap the carry chain)
+    std::vector<uint32_t> stream_split_{70, 30}; // streamed output: per cent of the positions per group (eagen_ctx_set_stream_split)
+    DevBuf sh_planes_, sh_table_;
+    void ensure_comm_stream() { if (!nst_) { use(); EAGEN_CUDA(cudaStreamCreateWithFlags(&nst_, cudaStreamNonBlocking)); } }
     PinnedRing ring_;
     int* d_one_ = nullptr;
     uint64_t launches_ = 0;
@@ -1115,9 +1270,14 @@ private:
             launch2d(k_count_nonzero, dim3(chunks, d), 256, planes, n, chunks, cnt);
             launch(k_scan_chunks<FB>, d, 64, cnt, chunks, d, (uint32_t)base, carries, tree_n);
         }
-        std::vector<int> hn(d);
-        EAGEN_CUDA(cudaMemcpyAsync(hn.data(), tree_n, (size_t)d * sizeof(int), cudaMemcpyDeviceToHost, st_));
+        // list lengths (they size everything below) and, in the same round trip, the error flag of K1: a scalar out of range fails
+        // here, before any tree is built or streamed (the reference asserts before any work, src/argument_witness_calc.rs:97)
+        int* hstage = (int*)ring_.take((size_t)(d + 1) * sizeof(int));
+        EAGEN_CUDA(cudaMemcpyAsync(hstage, tree_n, (size_t)d * sizeof(int), cudaMemcpyDeviceToHost, st_));
+        EAGEN_CUDA(cudaMemcpyAsync(hstage + d, d_err_, sizeof(int), cudaMemcpyDeviceToHost, st_));
         EAGEN_CUDA(cudaStreamSynchronize(st_));
+        if (hstage[d] & (KERR_RANGE | KERR_DIGITS)) sync_check();   // throws with the proper status
+        std::vector<int> hn(hstage, hstage + d);
         size_t nmax = 1;
         for (uint32_t p = pos_begin; p < pos_end; ++p) nmax = std::max<size_t>(nmax, (size_t)hn[p]);
         // result slots sized for the deepest tree of the range
@@ -1135,21 +1295,12 @@ private:
         size_t budget = (size_t)((double)(free_b + pooled_bytes()) * 0.80);
         uint32_t group = (uint32_t)std::max<size_t>(1, std::min<size_t>(npos, budget / std::max<size_t>(per_tree, 1)));
         // group sizes: as large as the memory budget allows; for streamed output a decreasing schedule (per cent of the positions,
-        // EAGEN_STREAM_SPLIT, default 70,30) so that every group's copy hides behind the next group's compute and only the
+        // eagen_ctx_set_stream_split, default 70,30) so that every group's copy hides behind the next group's compute and only the
         // small last group's copy is exposed.  More, smaller groups shorten the exposed copy but add ~1300 launches each:
         // 70,30 measured 3 ms faster than 60,30,10 on boxes with a fast host link (tools/e2e_groups.py)
         std::vector<uint32_t> sizes;
         if (so) {
-            std::vector<uint32_t> pct;
-            const char* e = getenv("EAGEN_STREAM_SPLIT");
-            std::string spec = e ? e : "70,30";
-            for (size_t i = 0; i < spec.size();) {
-                size_t j = spec.find(',', i);
-                if (j == std::string::npos) j = spec.size();
-                int v = atoi(spec.substr(i, j - i).c_str());
-                if (v > 0) pct.push_back((uint32_t)v);
-                i = j + 1;
-            }
+            const std::vector<uint32_t>& pct = stream_split_;
             uint32_t left = npos;
             for (size_t i = 0; i < pct.size() && left; ++i) {
                 uint32_t want = i + 1 == pct.size() ? left : std::min<uint32_t>(left, std::max<uint32_t>(1, (npos * pct[i] + 50) / 100));

@@ -15,6 +15,14 @@
  *
  * All functions return EAGEN_OK (0) or a negative error code; nothing here ever falls back to a CPU path.
  * A context is bound to one CUDA device and is not thread-safe (use one context per thread).
+ *
+ * Preconditions every entry point relies on:
+ *   - curves with a = 0 only (y^2 = x^3 + b).  The reference is generic in C::a() (subst_y2 = [B, A, 0, 1],
+ *     src/regular_functions_utils.rs:270); the three curve ids below all have a = 0 and the kernels assume it.  There is no
+ *     way to pass another curve: an unknown curve id is EAGEN_E_ARG.
+ *   - stream ordering of the eagen_dev_* entry points: the library launches on its own non-blocking streams.  Device buffers
+ *     passed in must be COMPLETE (the producing stream synchronised, or an event the caller has already waited on) before the
+ *     call; every call returns only after its own device work has finished, so outputs may be used from any stream afterwards.
  */
 #ifndef EAGEN_MSM_H
 #define EAGEN_MSM_H
@@ -43,7 +51,7 @@ enum eagen_status {
     EAGEN_E_SUM_NONZERO = -4,   /* points do not sum to the identity       src/regular_functions_utils.rs:478    */
     EAGEN_E_NTT_TOO_LARGE = -5, /* F::S < loglength                        src/regular_functions_utils.rs:110    */
     EAGEN_E_CUDA = -6,          /* CUDA runtime error (see eagen_last_error)                                     */
-    EAGEN_E_NCCL = -7,          /* reserved for the collective layer                                             */
+    EAGEN_E_NCCL = -7,          /* NCCL failure, libnccl.so.2 not loadable, or a sharded call without a communicator     */
     EAGEN_E_DIGITS = -8,        /* negbase expansion longer than d digits (the reference truncates silently, :99) */
     EAGEN_E_DOMAIN = -9,        /* an intermediate point's x lies on the power-of-two evaluation domain even after the
                                    trees were rebuilt on four isomorphic curves (see eagen_fallback_count)          */
@@ -67,6 +75,9 @@ enum eagen_which { EAGEN_POLY_A = 0, EAGEN_POLY_B = 1 };
 /* ---- context ------------------------------------------------------------------------------------------ */
 int eagen_ctx_create(int curve, int device, eagen_ctx** out);
 void eagen_ctx_destroy(eagen_ctx* ctx);
+/* streamed output (eagen_lhs_witness_stream / _sharded): per cent of the digit positions per group, e.g. {70, 30} (the default) or
+ * {60, 30, 10} on a slow host link; every group's copy hides behind the next group's kernels.  n = 0 restores the default. */
+int eagen_ctx_set_stream_split(eagen_ctx* ctx, const uint32_t* percent, int n);
 const char* eagen_last_error(const eagen_ctx* ctx);   /* message of the last failing call (never NULL)        */
 const char* eagen_status_string(int status);
 /* number of kernels this context has launched so far (bench.py reports the per-step delta as gpu_launches) */
@@ -209,6 +220,39 @@ int eagen_batch_invert(eagen_ctx* ctx, uint64_t* elems, size_t n);
  * pts: n Jacobian points; out: n field elements (0 for identity points)                                     */
 int eagen_eval_function(eagen_ctx* ctx, const uint64_t* a, size_t la, const uint64_t* b, size_t lb,
                         const uint64_t* pts, size_t n, uint64_t* out);
+
+/* ---- multi-GPU: compute_lhs_witness sharded over the GPUs of one box ----------------------
+ * The reference API is ONE call (src/argument_witness_calc.rs:87); here every rank (one context per GPU; one host thread or process
+ * per context) makes the same call with ITS contiguous share of the points and gets back the functions of ITS share of the digit
+ * positions.  Inside the call: K1-K3 on the local point range, ncclAllGather of the d partial digit sums / the digit planes / the
+ * multiples table on the library's communication stream, the replicated carry chain (overlapping the gathers), then the trees of
+ * positions eagen_position_range(rank).  libnccl.so.2 is resolved at run time; EAGEN_E_NCCL if it is missing or a collective fails.
+ *
+ *   multi-process : rank 0 calls eagen_comm_unique_id, ships the 128 bytes to the other ranks (any side channel), every rank calls
+ *                   eagen_comm_init(ctx, nranks, rank, id).
+ *   one process   : eagen_comm_init_all(ctxs, n) (ncclCommInitAll over the contexts' devices); the sharded call must then be issued
+ *                   from n host threads, one per context.
+ * Every rank must pass the same n_local (pad the last share with zero scalars: a zero scalar contributes nothing); EAGEN_E_LEN
+ * otherwise.  Result: function slot s of the returned handle is digit position eagen_result_first_function(res) + s of the whole
+ * witness; eagen_result_carry / _carries are the global ones on every rank. */
+#define EAGEN_COMM_ID_BYTES 128
+int eagen_comm_unique_id(void* id_out /* EAGEN_COMM_ID_BYTES */);
+int eagen_comm_init(eagen_ctx* ctx, int nranks, int rank, const void* unique_id);
+int eagen_comm_init_all(eagen_ctx** ctxs, int n);
+int eagen_comm_destroy(eagen_ctx* ctx);
+int eagen_comm_size(const eagen_ctx* ctx);
+int eagen_comm_rank(const eagen_ctx* ctx);
+/* digit positions (of the MSD-first iteration order) whose trees rank `rank` of `nranks` builds: [begin, end) */
+int eagen_position_range(int rank, int nranks, uint32_t d, uint32_t* begin, uint32_t* end);
+/* host buffers in; with out != NULL this rank's functions are streamed into `out` (layout of eagen_lhs_witness_stream over the local
+ * slots, sizes from eagen_lhs_witness_sharded_layout) while later positions are still being computed */
+int eagen_lhs_witness_sharded_layout(int curve, size_t n_total, uint8_t base, int rank, int nranks, size_t* a_stride, size_t* b_stride, size_t* total_bytes);
+int eagen_lhs_witness_sharded(eagen_ctx* ctx, const uint64_t* scalars_local, const uint64_t* pts_local, size_t n_local, uint8_t base,
+                              uint32_t flags, void* out, size_t out_bytes, eagen_result** res);
+/* device-resident inputs */
+int eagen_dev_lhs_witness_sharded(eagen_ctx* ctx, const void* d_scalars_local, const void* d_pts_local, size_t n_local, uint8_t base,
+                                  uint32_t flags, eagen_result** res);
+size_t eagen_result_first_function(const eagen_result* r);
 
 /* ---- synthetic inputs (tests / bench.py) ------------------------------------------------
  * n scalars uniform in [0, 2^k), 2^k <= isqrt(order) (k = 127 on Pasta, 126 on Grumpkin; Montgomery, scalar field) and n distinct points (a + j*b)*G as Jacobian triples

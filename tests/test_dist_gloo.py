@@ -1,6 +1,7 @@
 """CPU test of the multi-GPU host logic (not gpu): world_size 2 over gloo.  Checks the sharding plan the NCCL driver
-uses (halo2-liam-eagen-msm_b200/sharded.py): position ranges are a partition, all-gathered per-rank digit planes
-re-assemble into the global position-major planes, and per-rank partial digit sums combine to the global sums
+uses (eagen_lhs_witness_sharded in libeagen_msm.so; host mirror in halo2-liam-eagen-msm_b200/sharded.py): position ranges
+(the library's own eagen_position_range) are a partition, per-position all-gathers of the per-rank digit planes land as the global
+position-major planes, and per-rank partial digit sums combine to the global sums
 (the oracle plays the ranks' arithmetic here; on the GPU box the same plan runs over NCCL)."""
 import os
 
@@ -21,7 +22,7 @@ def _worker(rank, world, port, n_local, ret):
     from conftest import load_eagen
     import oracle_lib
     eg = load_eagen()
-    from eagen_b200.sharded import merge_planes, position_range
+    from eagen_b200.sharded import gather_planes_rowwise, position_range
     cv = pyref.Curve("pallas")
     base, d = 5, pyref.num_digits(cv, 5)
     rng = pyref.SplitMix64(99)
@@ -44,12 +45,10 @@ def _worker(rank, world, port, n_local, ret):
                 acc = cv.add(acc, cv.mul(dg, pts[lo + j]))
         sums.append(acc)
     packed = torch.from_numpy(oracle_lib.pack_points(sums, cv.p).astype(np.int64))
-    all_planes = torch.empty(world * d * n_local, dtype=torch.uint8)
-    dist.all_gather_into_tensor(all_planes, planes_local.reshape(-1))
     all_sums = torch.empty(world * packed.numel(), dtype=torch.int64)
     dist.all_gather_into_tensor(all_sums, packed.reshape(-1))
     all_sums = all_sums.view(world, d, 12)
-    planes = merge_planes(all_planes, world, d, n_local)
+    planes = gather_planes_rowwise(dist, planes_local)   # what the library does with one grouped ncclAllGather per position row
     # global truth
     Sg, Pg = oracle_lib.pack_felts(sc, cv.q), oracle_lib.pack_points(pts, cv.p)
     g = oracle_lib.lhs_witness(0, Sg, Pg, base, with_functions=False)
