@@ -209,7 +209,7 @@ uint64_t eagen_launch_count(const eagen_ctx* ctx) { return ctx ? ctx->eng->launc
 uint64_t eagen_fallback_count(const eagen_ctx* ctx) { return ctx ? ctx->eng->iso_fallbacks() : 0; }
 
 int eagen_microbench(eagen_ctx* ctx, int which, double* ops_per_second) {
-    if (!ctx || !ops_per_second || which < 0 || which > 1) return EAGEN_E_ARG;
+    if (!ctx || !ops_per_second || which < 0 || which > 2) return EAGEN_E_ARG;
     return guarded(ctx, [&] { *ops_per_second = ctx->eng->microbench(which); });
 }
 int eagen_set_profiling(eagen_ctx* ctx, int on) {

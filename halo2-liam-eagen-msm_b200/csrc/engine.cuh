@@ -676,7 +676,7 @@ public:
         return res.release();
     }
 
-    // which = 0: 32-bit IMAD per second; which = 1: base-field Montgomery products per second (register-resident chains)
+    // which = 0: 32-bit IMAD per second; 1: base-field Montgomery products per second (register-resident chains); 2: IMAD.WIDE per second
     double microbench(int which) override {
         use();
         int sms = 0;
@@ -685,16 +685,17 @@ public:
         void* buf = den_.ensure((size_t)blocks * threads * 32);
         double best = 0;
         for (int rep = 0; rep < 4; ++rep) {
-            const int iters = which == 0 ? 4096 : 512;
+            const int iters = which == 1 ? 512 : 4096;
             EAGEN_CUDA(cudaEventRecord(ev0_, st_));
             if (which == 0) k_imad_peak<<<blocks, threads, 0, st_>>>((uint32_t*)buf, iters, 12345u + rep);
+            else if (which == 2) k_imad_wide_peak<<<blocks, threads, 0, st_>>>((uint32_t*)buf, iters, 12345u + rep);
             else k_modmul_peak<FB><<<blocks, threads, 0, st_>>>((F*)buf, iters);
             ++launches_;
             EAGEN_CUDA(cudaGetLastError());
             EAGEN_CUDA(cudaEventRecord(ev1_, st_));
             EAGEN_CUDA(cudaStreamSynchronize(st_));
             float ms = 0; EAGEN_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
-            double ops = (double)blocks * threads * (double)iters * (which == 0 ? 128.0 : 4.0);
+            double ops = (double)blocks * threads * (double)iters * (which == 0 ? 128.0 : which == 2 ? 64.0 : 4.0);
             best = std::max(best, ops / (ms * 1e-3));
         }
         return best;
@@ -999,11 +1000,13 @@ private:
         Scope(Engine* e, const char* name, double bytes, double modmul) : eng(e), live(e->prof_on_) {
             if (!live) return;
             int tag;
-            if (eng->prof_detail_ && eng->prof_level_ >= 0) {
-                char buf[96];
-                snprintf(buf, sizeof buf, "%s@L%02d", name, eng->prof_level_);
-                tag = eng->prof_tag(buf);
-            } else tag = eng->prof_tag(name);
+            char buf[112];
+            // launches issued to the side stream overlap the main stream's kernels: their event times are not additive with the
+            // rest, so they are booked under their own name ("pair_points~side")
+            const char* side = eng->ls_ != eng->st_ ? "~side" : "";
+            if (eng->prof_detail_ && eng->prof_level_ >= 0) snprintf(buf, sizeof buf, "%s%s@L%02d", name, side, eng->prof_level_);
+            else snprintf(buf, sizeof buf, "%s%s", name, side);
+            tag = eng->prof_tag(buf);
             eng->prof_[tag].bytes += bytes; eng->prof_[tag].modmul += modmul; eng->prof_[tag].scopes += 1;
             ProfPending p; p.tag = tag; p.a = eng->get_event(); p.b = eng->get_event(); p.l0 = eng->launches_; p.l1 = 0;
             p.st = eng->ls_;

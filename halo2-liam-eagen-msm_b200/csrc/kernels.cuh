@@ -961,6 +961,50 @@ __global__ void k_den(const MergeDesc<FP>* __restrict__ desc, size_t nmerges, in
 #endif
 // ISO: the tree is being built on the isomorphic curve y^2 = x^3 + u^6 b (collision fallback, see Engine::run_trees_safe), whose
 // right-hand side is the tabulated x^3 + b plus the constant gshift = (u^6 - 1) b.
+// one evaluation point g = (merge m, position p) of the merge; `di` = 1 / ((x - alpha)(x - beta)) there (read only by generic merges)
+template <class CC, bool ISO>
+EAGEN_D void pointwise_at(const MergeDesc<typename CC::Base>* __restrict__ desc, size_t g, int t, uint32_t mode,
+                          const Fe<typename CC::Base>* __restrict__ xt, const Fe<typename CC::Base>* __restrict__ gt,
+                          const Fe<typename CC::Base>* __restrict__ EA, const Fe<typename CC::Base>* __restrict__ EB,
+                          const Fe<typename CC::Base>& di, size_t merges_per_tree, size_t nodes_per_tree,
+                          Fe<typename CC::Base>* __restrict__ OA, Fe<typename CC::Base>* __restrict__ OB, size_t out_stride,
+                          const Fe<typename CC::Base>& gshift) {
+    typedef typename CC::Base F;
+    size_t m = g >> t;
+    uint32_t p = (uint32_t)(g & (((size_t)1 << t) - 1));
+    const uint32_t tree32 = (uint32_t)m / (uint32_t)merges_per_tree;   // merge index < 2^32
+    size_t tree = tree32, j = (uint32_t)m - tree32 * (uint32_t)merges_per_tree;
+    size_t c1 = ((tree * nodes_per_tree + 2 * j) << t) + p, c2 = c1 + ((size_t)1 << t);
+    Fe<F> a1 = ldg(EA + c1), b1 = ldg(EB + c1);
+    Fe<F> ra, rb;
+    if (mode == MERGE_PASS) {
+        ra = a1; rb = b1;
+    } else {
+        Fe<F> a2 = ldg(EA + c2), b2 = ldg(EB + c2);
+        Fe<F> gx = ldg(gt + p);
+        if (ISO) gx = add(gx, gshift);
+        // products of the form (u + y v)(u' + y v') = (u u' + v v' g) + y (u v' + v u') with three multiplications for the
+        // cross term (Karatsuba): 4 instead of 5 field products each
+        if (mode == MERGE_SHORTCUT) {
+            Fe<F> q1 = mul(a1, a2), q2 = mul(b1, b2), q3 = mul(add(a1, b1), add(a2, b2));
+            ra = add(q1, mul(q2, gx));
+            rb = sub(sub(q3, q1), q2);
+        } else {
+            Fe<F> x = ldg(xt + p);
+            Fe<F> lam = add(ldg(&desc[m].lz), mul(ldg(&desc[m].lx), x));
+            Fe<F> ly = ldg(&desc[m].ly);
+            Fe<F> p1 = mul(a2, lam), p2 = mul(b2, ly), p3 = mul(add(a2, b2), add(lam, ly));
+            Fe<F> U = add(p1, mul(p2, gx));
+            Fe<F> V = sub(sub(p3, p1), p2);
+            Fe<F> q1 = mul(a1, U), q2 = mul(b1, V), q3 = mul(add(a1, b1), add(U, V));
+            ra = mul(add(q1, mul(q2, gx)), di);
+            rb = mul(sub(sub(q3, q1), q2), di);
+        }
+    }
+    stg(OA + m * out_stride + p, ra);
+    stg(OB + m * out_stride + p, rb);
+}
+
 template <class CC, bool ISO>
 __global__ void __launch_bounds__(128, EAGEN_PW_MINBLOCKS)
 k_pointwise(const MergeDesc<typename CC::Base>* __restrict__ desc, size_t nmerges, int t,
@@ -973,42 +1017,11 @@ k_pointwise(const MergeDesc<typename CC::Base>* __restrict__ desc, size_t nmerge
     typedef typename CC::Base F;
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (nmerges << t)) return;
-    size_t m = g >> t;
-    uint32_t p = (uint32_t)(g & (((size_t)1 << t) - 1));
-    uint32_t mode = desc[m].mode;
+    uint32_t mode = desc[g >> t].mode;
     if (mode == MERGE_ABSENT) return;
-    const uint32_t tree32 = (uint32_t)m / (uint32_t)merges_per_tree;   // merge index < 2^32
-    size_t tree = tree32, j = (uint32_t)m - tree32 * (uint32_t)merges_per_tree;
-    size_t c1 = ((tree * nodes_per_tree + 2 * j) << t) + p, c2 = c1 + ((size_t)1 << t);
-    Fe<F> a1 = ldg(EA + c1), b1 = ldg(EB + c1);
-    Fe<F> ra, rb;
-    if (mode == MERGE_PASS) {
-        ra = a1; rb = b1;
-    } else {
-        Fe<F> a2 = ldg(EA + c2), b2 = ldg(EB + c2);
-        Fe<F> x = ldg(xt + p);
-        Fe<F> gx = ldg(gt + p);
-        if (ISO) gx = add(gx, gshift);
-        // products of the form (u + y v)(u' + y v') = (u u' + v v' g) + y (u v' + v u') with three multiplications for the
-        // cross term (Karatsuba): 4 instead of 5 field products each
-        if (mode == MERGE_SHORTCUT) {
-            Fe<F> q1 = mul(a1, a2), q2 = mul(b1, b2), q3 = mul(add(a1, b1), add(a2, b2));
-            ra = add(q1, mul(q2, gx));
-            rb = sub(sub(q3, q1), q2);
-        } else {
-            Fe<F> lam = add(ldg(&desc[m].lz), mul(ldg(&desc[m].lx), x));
-            Fe<F> ly = ldg(&desc[m].ly);
-            Fe<F> p1 = mul(a2, lam), p2 = mul(b2, ly), p3 = mul(add(a2, b2), add(lam, ly));
-            Fe<F> U = add(p1, mul(p2, gx));
-            Fe<F> V = sub(sub(p3, p1), p2);
-            Fe<F> q1 = mul(a1, U), q2 = mul(b1, V), q3 = mul(add(a1, b1), add(U, V));
-            Fe<F> di = ldg(dinv + g);
-            ra = mul(add(q1, mul(q2, gx)), di);
-            rb = mul(sub(sub(q3, q1), q2), di);
-        }
-    }
-    stg(OA + m * out_stride + p, ra);
-    stg(OB + m * out_stride + p, rb);
+    Fe<F> di = Fe<F>::zero();
+    if (mode == MERGE_GENERIC) di = ldg(dinv + g);
+    pointwise_at<CC, ISO>(desc, g, t, mode, xt, gt, EA, EB, di, merges_per_tree, nodes_per_tree, OA, OB, out_stride, gshift);
 }
 
 // The parent's a has T+1 coefficients but the transform has T points: the top coefficient q_T aliases
@@ -1554,6 +1567,29 @@ static __global__ void k_imad_peak(uint32_t* out, int iters, uint32_t seed) {
     uint32_t x = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) x ^= a[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+// 16 independent carry-chained 32x32+64 multiply-accumulates per thread (mad.lo.cc / madc.hi pairs, the form the Montgomery
+// product issues: ptxas fuses each pair into one IMAD.WIDE.U32) -> IMAD.WIDE per second: the multiplier-pipe ceiling
+static __global__ void k_imad_wide_peak(uint32_t* out, int iters, uint32_t seed) {
+    uint32_t lo[16], hi[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { lo[i] = seed + threadIdx.x * 16 + i; hi[i] = seed * 3 + i; }
+    uint32_t m = seed | 1;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                unsigned long long t = (unsigned long long)lo[i] * m + (((unsigned long long)hi[i] << 32) | lo[i]);
+                lo[i] = (uint32_t)t; hi[i] = (uint32_t)(t >> 32);
+            }
+        }
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x ^= lo[i] ^ hi[i];
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x;
 }
 

@@ -1,6 +1,6 @@
 //! Raw bindings to include/eagen_msm.h (hand-written; one declaration per C entry point the shim uses).
 #![allow(non_camel_case_types)]
-use std::os::raw::{c_char, c_int};
+use std::os::raw::{c_char, c_int, c_void};
 
 #[repr(C)] pub struct eagen_ctx { _private: [u8; 0] }
 #[repr(C)] pub struct eagen_result { _private: [u8; 0] }
@@ -48,6 +48,16 @@ extern "C" {
     pub fn eagen_to_curve_x(curve: c_int, c: *const u64, x_out: *mut u64) -> c_int;
     pub fn eagen_y_from_x(curve: c_int, x: *const u64, y_out: *mut u64, is_square: *mut c_int) -> c_int;
     pub fn eagen_slope(curve: c_int, xy: *const u64, slope_out: *mut u64) -> c_int;
+    // multi-GPU (include/eagen_msm.h, "multi-GPU" section)
+    pub fn eagen_comm_unique_id(id_out: *mut u8) -> c_int;
+    pub fn eagen_comm_init(ctx: *mut eagen_ctx, nranks: c_int, rank: c_int, unique_id: *const u8) -> c_int;
+    pub fn eagen_comm_init_all(ctxs: *mut *mut eagen_ctx, n: c_int) -> c_int;
+    pub fn eagen_comm_destroy(ctx: *mut eagen_ctx) -> c_int;
+    pub fn eagen_position_range(rank: c_int, nranks: c_int, d: u32, begin: *mut u32, end: *mut u32) -> c_int;
+    pub fn eagen_lhs_witness_sharded(ctx: *mut eagen_ctx, scalars: *const u64, pts: *const u64, n_local: usize, base: u8, flags: u32,
+                                     out: *mut c_void, out_bytes: usize, res: *mut *mut eagen_result) -> c_int;
+    pub fn eagen_result_first_function(r: *const eagen_result) -> usize;
+    pub fn eagen_ctx_set_stream_split(ctx: *mut eagen_ctx, percent: *const u32, n: c_int) -> c_int;
 }
 
 /// one entry of eagen_prepare_scalar_witness (32 bytes, see include/eagen_msm.h)

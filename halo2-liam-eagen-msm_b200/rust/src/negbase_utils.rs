@@ -1,7 +1,7 @@
-//! reference: src/negbase_utils.rs.  The scalar loop of `negbase_decompose` is a host-side helper in the reference
-//! too; the batched GPU entry point is what `compute_lhs_witness` uses.  `range_check`, `id_by_digit`, `digit_by_id`,
-//! `table_entry_by_id` and the single-scalar `prepare_scalar_witness` are pure host code in the reference and are kept verbatim
-//! by the integrating crate (not reproduced here); the batched form below fills the same `Entry` rows for all scalars at once.
+//! reference: src/negbase_utils.rs.  Every public name of the reference module is here with its signature, so `config.rs`
+//! (`use crate::negbase_utils::{self, digit_by_id, table_entry_by_id}`, reference: src/config.rs:13,342,486) compiles against
+//! this module unchanged.  The scalar loop of `negbase_decompose` and the index helpers are host code in the reference too;
+//! the batched GPU entry points are what `compute_lhs_witness` and the circuit's column b use.
 use crate::ffi::*;
 use crate::gpu::*;
 use ff::PrimeField;
@@ -21,6 +21,39 @@ pub fn negbase_decompose(x: &BigInt, base: u8) -> Vec<u8> {
         x = -((x - digit) / base);
     }
     acc
+}
+
+/// reference: :11-15
+pub fn range_check(x: &BigInt) {
+    let threshold = BigInt::from(1u8) << 127;
+    assert!(x < &threshold);
+    assert!(x > &-threshold);
+}
+
+/// reference: :46-51 -- index of a digit in the multiples table, None for digit 0
+pub fn id_by_digit(digit: u8) -> Option<usize> { if digit == 0 { None } else { Some(digit as usize - 1) } }
+/// reference: :54-56
+pub fn digit_by_id(id: usize) -> u8 { u8::try_from(id + 1).unwrap() }
+
+/// reference: :58-77 -- Horner over the bits of `id`, most significant first, in base (-base), with one trailing factor:
+/// sum_k bit_k (-base)^(k+1).  Generic host code like the reference's (config.rs instantiates it with bn256::Fr);
+/// `eagen_table_entry_by_id` gives the same value for the library's base fields and is what the parity tests pin.
+pub fn table_entry_by_id<F: PrimeField>(base: u8, id: usize) -> F {
+    let nb = -F::from(base as u64);
+    let width = usize::BITS - id.leading_zeros();
+    (0..width).rev().fold(F::ZERO, |acc, k| (acc + if (id >> k) & 1 == 1 { F::ONE } else { F::ZERO }) * nb)
+}
+
+/// reference: :79-124 -- one scalar; the rows come from the device kernel through the batched call (Pallas scalar field: the
+/// admissible scalars are < 2^127 + 2 and fit every instantiated field).  Faithful limb indexing, as the reference is written.
+pub fn prepare_scalar_witness(sc: &BigInt, base: u8, num_digits: usize, logtable: usize) -> Vec<Vec<Entry>> {
+    use halo2curves::pasta::{pallas, Fq};
+    let (sign, bytes) = sc.to_bytes_le();
+    assert!(sign != Sign::Minus, "prepare_scalar_witness: negative scalar");
+    let mut repr = <Fq as PrimeField>::Repr::default();
+    repr.as_mut()[..bytes.len()].copy_from_slice(&bytes);
+    let s = Fq::from_repr(repr).unwrap();
+    prepare_scalar_witness_batch::<pallas::Point>(&[s], base, num_digits, logtable, false).pop().unwrap()
 }
 
 /// Batched form used by the path: `n x d` digits, MSD first (what argument_witness_calc.rs:99-101 builds).

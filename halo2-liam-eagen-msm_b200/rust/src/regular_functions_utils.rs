@@ -4,7 +4,7 @@ use crate::ffi::*;
 use crate::gpu::*;
 use ff::PrimeField;
 use halo2curves::CurveExt;
-use std::ops::Mul;
+use std::ops::{Add, Mul, Shr};
 
 /// reference: :17-24.  The reference only implements this for bn256::Fr (src/precomputed_fft_data.rs); the library
 /// derives the Pasta tables from ROOT_OF_UNITY with the same recipe (src/scripts.rs:44-70).
@@ -41,6 +41,34 @@ impl<F: PrimeField + FftPrecomp> Polynomial<F> {
         Polynomial::new(q)
     }
     pub fn scale(&self, sc: F) -> Self { Polynomial::new(self.poly.iter().map(|x| *x * sc).collect()) }
+    /// reference: :54-62 (schoolbook; the reference underflows `usize` on two empty operands, kept)
+    pub fn mul_naive(a: &Self, b: &Self) -> Self {
+        let mut out = vec![F::ZERO; a.poly.len() + b.poly.len() - 1];
+        for (i, x) in a.poly.iter().enumerate() { for (j, y) in b.poly.iter().enumerate() { out[i + j] += *x * y; } }
+        Polynomial::new(out)
+    }
+}
+impl<F: PrimeField + FftPrecomp + BaseFieldOf> Polynomial<F> {
+    /// reference: :102-129 -- same result (exact arithmetic), computed by the device transform (eagen_poly_mul)
+    pub fn mul_fft(&self, other: &Self) -> Self { self * other }
+}
+/// reference: :31-33
+pub fn poly<T: IntoIterator>(it: T) -> Polynomial<T::Item> where T::Item: PrimeField + FftPrecomp { Polynomial::new(it.into_iter().collect()) }
+
+/// reference: :167-175 -- multiplication by x^k
+impl<F: PrimeField + FftPrecomp> Shr<usize> for &Polynomial<F> {
+    type Output = Polynomial<F>;
+    fn shr(self, k: usize) -> Polynomial<F> { Polynomial::new(std::iter::repeat(F::ZERO).take(k).chain(self.poly.iter().cloned()).collect()) }
+}
+/// reference: :178-195 -- coefficient-wise sum, length of the longer operand
+impl<F: PrimeField + FftPrecomp> Add for &Polynomial<F> {
+    type Output = Polynomial<F>;
+    fn add(self, other: Self) -> Polynomial<F> {
+        let (long, short) = if self.poly.len() >= other.poly.len() { (self, other) } else { (other, self) };
+        let mut out = long.poly.clone();
+        for (o, s) in out.iter_mut().zip(short.poly.iter()) { *o += s; }
+        Polynomial::new(out)
+    }
 }
 
 /// `&Polynomial * &Polynomial` (reference: :209-216) -> eagen_poly_mul.  `curve_of::<F>()` picks the context whose BASE
@@ -77,6 +105,83 @@ impl<C: CurveExt> RegularFunction<C> where C::Base: FftPrecomp {
     }
     pub fn ev_unchecked(&self, x: C::Base, y: C::Base) -> C::Base { self.a.ev(x) + self.b.ev(x) * y }
     pub fn scale(&self, sc: C::Base) -> Self { RegularFunction { a: self.a.scale(sc), b: self.b.scale(sc) } }
+    /// reference: :239-242
+    pub fn from_const(x: C::Base) -> Self { RegularFunction { a: Polynomial::new(vec![x]), b: Polynomial::new(vec![]) } }
+    /// reference: :244-246 -- the line a*x + b*y + c
+    pub fn from_line(a: C::Base, b: C::Base, c: C::Base) -> Self { RegularFunction { a: Polynomial::new(vec![c, a]), b: Polynomial::new(vec![b]) } }
+}
+/// reference: :257-264
+impl<C: CurveExt> Add for &RegularFunction<C> where C::Base: FftPrecomp {
+    type Output = RegularFunction<C>;
+    fn add(self, other: Self) -> RegularFunction<C> { RegularFunction { a: &self.a + &other.a, b: &self.b + &other.b } }
+}
+/// reference: :266-273 -- (a + y b)(a' + y b') with y^2 -> x^3 + A x + B
+impl<C: CurveExt> Mul for &RegularFunction<C> where C::Base: FftPrecomp + BaseFieldOf {
+    type Output = RegularFunction<C>;
+    fn mul(self, other: Self) -> RegularFunction<C> {
+        let y2 = Polynomial::new(vec![C::b(), C::a(), C::Base::ZERO, C::Base::ONE]);
+        let bb = &(&self.b * &other.b) * &y2;
+        RegularFunction { a: &(&self.a * &other.a) + &bb, b: &(&self.a * &other.b) + &(&self.b * &other.a) }
+    }
+}
+
+/// reference: :426-431 -- (X Z, Y, Z^3) of the Jacobian triple: homogeneous coordinates of the same point
+pub fn projective_coords<C: CurveExt>(pt: &C) -> (C::Base, C::Base, C::Base) {
+    let (x, y, z) = pt.jacobian_coordinates();
+    (x * z, y, z.square() * z)
+}
+/// reference: :285-303 -- the line through a and b as the cross product of their homogeneous triples; when that vanishes
+/// (a == b) the tangent, i.e. the line through a and -(a + b)
+pub fn linefunc<C: CurveExt>(a: &C, b: &C) -> RegularFunction<C> where C::Base: FftPrecomp {
+    let cross = |p: (C::Base, C::Base, C::Base), q: (C::Base, C::Base, C::Base)| (p.1 * q.2 - p.2 * q.1, p.2 * q.0 - p.0 * q.2, p.0 * q.1 - p.1 * q.0);
+    let (pa, pb) = (projective_coords(a), projective_coords(b));
+    let mut l = cross(pa, pb);
+    if l.0 == C::Base::ZERO && l.1 == C::Base::ZERO && l.2 == C::Base::ZERO {
+        let c = -(*a + *b);
+        l = cross(pa, projective_coords(&c));
+    }
+    RegularFunction::from_line(l.0, l.1, l.2)
+}
+
+/// reference: :305-408 -- a partial witness: the function with divisor sum[inputs] + [output] - (n+1)[inf].  The tree the
+/// reference builds with group_merge is what eagen_divisor_witness runs on the device; these host forms keep the public type
+/// for callers that compose witnesses by hand.  `merge` follows :333-360 (identity shortcut, division by the two vertical lines).
+#[derive(Clone)]
+pub struct Propagation<C: CurveExt> where C::Base: FftPrecomp { pub inputs: Vec<C>, pub output: C, pub wtns: RegularFunction<C> }
+impl<C: CurveExt> Propagation<C> where C::Base: FftPrecomp + BaseFieldOf {
+    pub fn empty() -> Self { Propagation { inputs: vec![], output: C::identity(), wtns: RegularFunction::from_const(C::Base::ONE) } }
+    pub fn from_point(pt: C) -> Self {
+        if bool::from(pt.is_identity()) { return Self::empty(); }
+        Propagation { inputs: vec![pt], output: -pt, wtns: linefunc(&pt, &-pt) }
+    }
+    pub fn from_pair(p: C, q: C) -> Self {
+        if bool::from(p.is_identity()) { return Self::from_point(q); }
+        Propagation { inputs: vec![p, q], output: -(p + q), wtns: linefunc(&p, &q) }
+    }
+    pub fn merge(a: Self, b: Self) -> Self {
+        let output = a.output + b.output;
+        let inputs = a.inputs.iter().chain(b.inputs.iter()).cloned().collect();
+        if bool::from(a.output.is_identity()) || bool::from(b.output.is_identity()) {
+            return Propagation { inputs, output, wtns: &a.wtns * &b.wtns };
+        }
+        let num = &a.wtns * &(&b.wtns * &linefunc(&-a.output, &-b.output));
+        let affine_x = |p: &C| { let (x, _, z) = p.jacobian_coordinates(); x * z.square().invert().unwrap() };
+        let (xa, xb) = (affine_x(&a.output), affine_x(&b.output));
+        let wtns = RegularFunction::new(num.a.kate_div(xa).kate_div(xb), num.b.kate_div(xa).kate_div(xb));
+        Propagation { inputs, output, wtns }
+    }
+    /// reference: :380-405 -- pair neighbours level by level, an odd tail passes through
+    pub fn group_merge(arr: Vec<Self>) -> Self {
+        assert!(!arr.is_empty());
+        let mut level = arr;
+        while level.len() > 1 {
+            let mut next = Vec::with_capacity((level.len() + 1) / 2);
+            let mut it = level.into_iter();
+            while let Some(x) = it.next() { next.push(match it.next() { Some(y) => Self::merge(x, y), None => x }); }
+            level = next;
+        }
+        level.pop().unwrap()
+    }
 }
 
 pub(crate) unsafe fn function_from_result<C: CurveExt>(res: *mut eagen_result, k: usize) -> RegularFunction<C> where C::Base: FftPrecomp + PrimeField {

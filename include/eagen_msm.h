@@ -91,7 +91,9 @@ uint64_t eagen_fallback_count(const eagen_ctx* ctx);
  * on = 0 off, 1 one entry per kernel group, 2 additionally split by tree level ("group@L07": the merge that builds level 8). */
 int eagen_set_profiling(eagen_ctx* ctx, int on);
 /* integer-pipe roofline denominators measured on this device: which = 0 -> dependent-free 32-bit IMAD per second,
- * which = 1 -> base-field Montgomery products per second in a register-resident loop (ceiling of the field code) */
+ * which = 1 -> base-field Montgomery products per second in a register-resident loop (ceiling of the field code),
+ * which = 2 -> IMAD.WIDE (32x32+64 multiply-accumulate) per second: divided by the 87 IMAD.WIDE of one product it is the multiplier-pipe
+ * ceiling every field kernel is measured against */
 int eagen_microbench(eagen_ctx* ctx, int which, double* ops_per_second);
 int eagen_profile_reset(eagen_ctx* ctx);
 int eagen_profile_json(eagen_ctx* ctx, char* buf, size_t cap);

@@ -48,6 +48,9 @@ def main():
             traffic[g][1] += n
     open(prefix + "_launches_summary.txt", "w").write("\n".join(out) + "\n")
     tj = {g: v[0] / max(v[1], 1) for g, v in traffic.items()}
+    nf, ni = traffic.get("ntt_forward", [0.0, 0]), traffic.get("ntt_inverse", [0.0, 0])
+    if nf[1] + ni[1]:   # both directions are the same kernel template: bench.py's roofline group
+        tj["k_ntt_pass"] = (nf[0] + ni[0]) / (nf[1] + ni[1])
     json.dump(tj, open("profiles/ncu_traffic.json", "w"), indent=1)
     print("\n".join(out[:14]))
     print(tj)

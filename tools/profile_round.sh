@@ -1,23 +1,26 @@
 #!/bin/bash
 # Round-end evidence in ONE gpurun call (1 GPU):  tools/profile_round.sh rNN
 #   1. plain bench (the number), reference arm, config-5 sweep            -> gpurun_out/<tag>_bench.json, _bench_reference.json, _sweep.json
-#   2. ncu launch list of one bench step (time + DRAM bytes per launch)   -> gpurun_out/<tag>_launches.csv
-#   3. ncu --set full of the top kernels (NTT passes, pointwise, binv; K1, K3, den) -> gpurun_out/<tag>_full_*.ncu-rep
-#      read here with: ncu -i <rep> --page raw --csv > profiles/<tag>_..._full_raw.csv
-# A number printed by a run under ncu is never a bench value; steps 2-3 only run if step 1 exited 0.
-TAG=${1:-r01}
+#   2. ncu launch list of one witness step (time + DRAM bytes per launch) -> gpurun_out/<tag>_launches.csv
+#   3. ncu --set full of every kernel >= 1 % of the step (NTT passes both directions, pointwise, binv up/down/base, fixup,
+#      merge_desc, pair_finish, den, digit sums, K1)                      -> gpurun_out/<tag>_full_*.ncu-rep (+ raw csv pages)
+# A number printed by a run under ncu is never a bench value; steps 2-3 only run if the same command exited 0 without ncu.
+TAG=${1:-r02}
 set -o pipefail
 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err || exit 1
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_reference.json 2>> gpurun_out/${TAG}_bench.err
 python tools/sweep.py > gpurun_out/${TAG}_sweep.json 2> gpurun_out/${TAG}_sweep.err
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e"
+CMD="python tools/one_step.py"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
     --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
-# one bench step has 246 launches matching the first regex (112 NTT passes, 19 pointwise, 115 binv_down): skip the warm-up step
-ncu --set full --clock-control none --import-source on -k regex:'k_ntt_pass|k_pointwise|k_binv_down' -s 330 -c 12 \
+# one witness step has ~60 NTT launches, 19 pointwise, ~110 binv_down: skip the warm-up step and the small bottom levels
+ncu --set full --clock-control none --import-source on -k regex:'k_ntt_pass|k_pointwise|k_binv_down|k_binv_up' -s 290 -c 14 \
     -o gpurun_out/${TAG}_full_ntt_pw $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'k_negbase|k_digit_sums|k_den' -c 4 \
-    -o gpurun_out/${TAG}_full_k1_k3 $CMD > gpurun_out/${TAG}_ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_negbase|k_digit_sums|k_den|k_fixup|k_merge_desc|k_pair_finish|k_binv_base|k_scatter_points' -s 40 -c 10 \
+    -o gpurun_out/${TAG}_full_small $CMD > gpurun_out/${TAG}_ncu3.log 2>&1
+for r in ntt_pw small; do
+  ncu -i gpurun_out/${TAG}_full_${r}.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_${r}_raw.csv 2>/dev/null
+done
 echo profile_round done
