@@ -1255,6 +1255,11 @@ private:
         Prj* cp = (Prj*)carries_proj_.ensure((size_t)d * sizeof(Prj));
         F* zs = (F*)lead_.ensure((size_t)d * 32);
         Scope ps(this, "carry_chain", (double)d * 96.0 * (nparts + 1), (double)d * (14.0 * nparts + 14.0 * 4));
+        if (nparts > 1) {   // fold the ranks' partial sums per position in parallel first: the serial chain stays d steps of one addition
+            Prj* folded = (Prj*)partials_.ensure((size_t)d * sizeof(Prj));
+            launch(k_sum_parts<CC>, d, 32, sums, d, nparts, folded);
+            sums = folded; nparts = 1;
+        }
         launch(k_carry_chain<CC>, 1, 32, sums, d, (uint32_t)base, nparts, cp, zs);
         batch_invert(zs, d);
         launch(k_proj_to_affine<FB>, d, 64, (const Prj*)cp, (const F*)zs, (size_t)d, carries);

@@ -400,6 +400,17 @@ k_reduce_partials(const Proj<typename CC::Base>* __restrict__ partials, int coun
     if (threadIdx.x == 0) out[pos] = sm[0];
 }
 
+// per-rank partial digit sums (multi-GPU all-gather: sums[part*d + i]) -> one sum per position, all positions in parallel, so the
+// serial chain below adds ONE point per step whatever the number of ranks
+template <class CC>
+__global__ void k_sum_parts(const Proj<typename CC::Base>* __restrict__ sums, uint32_t d, int nparts, Proj<typename CC::Base>* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    Proj<typename CC::Base> acc = sums[i];
+    for (int part = 1; part < nparts; ++part) acc = padd<CC>(acc, sums[(size_t)part * d + i]);
+    out[i] = acc;
+}
+
 // K4  Horner chain in base (-b): carry_i = b * (-carry_{i-1}) + S_i ; serial in i (d steps)
 template <class CC>
 __global__ void k_carry_chain(const Proj<typename CC::Base>* __restrict__ sums, uint32_t d, uint32_t base, int nparts,

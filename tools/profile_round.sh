@@ -3,7 +3,7 @@
 #   1. plain bench (the number), reference arm, config-5 sweep            -> gpurun_out/<tag>_bench.json, _bench_reference.json, _sweep.json
 #   2. ncu launch list of one witness step (time + DRAM bytes per launch) -> gpurun_out/<tag>_launches.csv
 #   3. ncu --set full of every kernel >= 1 % of the step (NTT passes both directions, pointwise, binv up/down/base, fixup,
-#      merge_desc, pair_finish, den, digit sums, K1)                      -> gpurun_out/<tag>_full_*.ncu-rep (+ raw csv pages)
+#      merge_desc, pair_finish, den, digit sums, K1)                      -> gpurun_out/<tag>_full_*_raw.csv (the .ncu-rep stay in /tmp: gpurun_out is capped at 64 MiB)
 # A number printed by a run under ncu is never a bench value; steps 2-3 only run if the same command exited 0 without ncu.
 TAG=${1:-r02}
 set -o pipefail
@@ -17,10 +17,10 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
 # one witness step has ~60 NTT launches, 19 pointwise, ~110 binv_down: skip the warm-up step and the small bottom levels
 ncu --set full --clock-control none --import-source on -k regex:'k_ntt_pass|k_pointwise|k_binv_down|k_binv_up' -s 290 -c 14 \
-    -o gpurun_out/${TAG}_full_ntt_pw $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
+    -o /tmp/${TAG}_full_ntt_pw $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k_negbase|k_digit_sums|k_den|k_fixup|k_merge_desc|k_pair_finish|k_binv_base|k_scatter_points' -s 40 -c 10 \
-    -o gpurun_out/${TAG}_full_small $CMD > gpurun_out/${TAG}_ncu3.log 2>&1
+    -o /tmp/${TAG}_full_small $CMD > gpurun_out/${TAG}_ncu3.log 2>&1
 for r in ntt_pw small; do
-  ncu -i gpurun_out/${TAG}_full_${r}.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_${r}_raw.csv 2>/dev/null
+  ncu -i /tmp/${TAG}_full_${r}.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_${r}_raw.csv 2>/dev/null
 done
 echo profile_round done

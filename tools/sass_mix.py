@@ -70,9 +70,10 @@ def kernels_of(obj):
 def short(name):
     # keep the kernel name and its template arguments readable
     name = re.sub(r"eagen::", "", name)
-    name = re.sub(r"\(.*$", "", name)
     name = re.sub(r"^void ", "", name)
-    return name
+    name = re.sub(r"\(bool\)", "", name)
+    m = re.match(r"([A-Za-z_0-9]+(?:<[^()]*?>)?)\(", name)   # kernel name + template arguments, parameter list dropped
+    return m.group(1) if m else re.sub(r"\(.*$", "", name)
 
 
 def main():
