@@ -583,7 +583,7 @@ public:
     void set_stream_split(const uint32_t* pct, int n) override {
         stream_split_.clear();
         for (int i = 0; i < n; ++i) if (pct[i] > 0) stream_split_.push_back(pct[i]);
-        if (stream_split_.empty()) { stream_split_.push_back(70); stream_split_.push_back(30); }
+        if (stream_split_.empty()) { stream_split_.push_back(75); stream_split_.push_back(25); }
     }
 
     // compute_lhs_witness over the point ranges of ALL ranks; this rank passes its own n_local scalars / points (every rank the same
@@ -638,13 +638,13 @@ public:
         }
         run_shard_sums(ds, dp, n_local, prm, pl_local, nullptr, tab_local, sums);
         // ---- the exchange, on the communication stream
-        EAGEN_CUDA(cudaEventRecord(sync_event(60), st_));
-        EAGEN_CUDA(cudaStreamWaitEvent(nst_, sync_event(60), 0));
+        EAGEN_CUDA(cudaEventRecord(sync_event(100), st_));
+        EAGEN_CUDA(cudaStreamWaitEvent(nst_, sync_event(100), 0));
         unsigned long long* hnl = (unsigned long long*)ring_.take((W + 1) * sizeof(unsigned long long));
         EAGEN_NCCL(nc.AllGather(nl, nl + 1, sizeof(unsigned long long), ncclUint8, comm_, nst_));
         EAGEN_CUDA(cudaMemcpyAsync(hnl, nl, (W + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, nst_));
         EAGEN_NCCL(nc.AllGather(sums, all_sums, (size_t)d * sizeof(Prj), ncclUint8, comm_, nst_));
-        EAGEN_CUDA(cudaEventRecord(sync_event(61), nst_));
+        EAGEN_CUDA(cudaEventRecord(sync_event(101), nst_));
         if (n_local) {
             // one all-gather per digit position, grouped into a single NCCL launch: row `pos` of every rank lands at its place in the
             // position-major planes over the global point range (no transpose pass afterwards)
@@ -654,14 +654,14 @@ public:
             EAGEN_NCCL(nc.GroupEnd());
             EAGEN_NCCL(nc.AllGather(tab_local, tab, n_local * (size_t)(base - 1) * 64, ncclUint8, comm_, nst_));
         }
-        EAGEN_CUDA(cudaEventRecord(sync_event(62), nst_));
+        EAGEN_CUDA(cudaEventRecord(sync_event(102), nst_));
         // ---- replicated carry chain while the planes / table are still in flight
-        EAGEN_CUDA(cudaStreamWaitEvent(st_, sync_event(61), 0));
+        EAGEN_CUDA(cudaStreamWaitEvent(st_, sync_event(101), 0));
         run_carry_chain(all_sums, nranks_, d, base, carries);
         res->carries.assign((size_t)d * 8, 0);
         uint64_t* hcar = (uint64_t*)ring_.take((size_t)d * 64);
         EAGEN_CUDA(cudaMemcpyAsync(hcar, carries, (size_t)d * 64, cudaMemcpyDeviceToHost, st_));
-        EAGEN_CUDA(cudaStreamWaitEvent(st_, sync_event(62), 0));
+        EAGEN_CUDA(cudaStreamWaitEvent(st_, sync_event(102), 0));
         EAGEN_CUDA(cudaStreamSynchronize(nst_));   // n_local of every rank is on the host now
         for (size_t r = 0; r < W; ++r)
             if (hnl[1 + r] != (unsigned long long)n_local)
@@ -1058,7 +1058,7 @@ private:
     int nranks_ = 1, rank_ = 0;
     bool comm_owned_ = false;
     cudaStream_t nst_ = nullptr;                 // communication stream (collectives overlap the carry chain)
-    std::vector<uint32_t> stream_split_{70, 30}; // streamed output: per cent of the positions per group (eagen_ctx_set_stream_split)
+    std::vector<uint32_t> stream_split_{75, 25}; // streamed output: per cent of the positions per group (eagen_ctx_set_stream_split)
     DevBuf sh_planes_, sh_table_;
     void ensure_comm_stream() { if (!nst_) { use(); EAGEN_CUDA(cudaStreamCreateWithFlags(&nst_, cudaStreamNonBlocking)); } }
     PinnedRing ring_;
@@ -1303,9 +1303,9 @@ private:
         size_t budget = (size_t)((double)(free_b + pooled_bytes()) * 0.80);
         uint32_t group = (uint32_t)std::max<size_t>(1, std::min<size_t>(npos, budget / std::max<size_t>(per_tree, 1)));
         // group sizes: as large as the memory budget allows; for streamed output a decreasing schedule (per cent of the positions,
-        // eagen_ctx_set_stream_split, default 70,30) so that every group's copy hides behind the next group's compute and only the
+        // eagen_ctx_set_stream_split, default 75,25) so that every group's copy hides behind the next group's compute and only the
         // small last group's copy is exposed.  More, smaller groups shorten the exposed copy but add ~1300 launches each:
-        // 70,30 measured 3 ms faster than 60,30,10 on boxes with a fast host link (tools/e2e_groups.py)
+        // measured (tools/e2e_groups.py, 2^20 Pallas, ms end to end): one group 328, 70/30 316, 75/25 315.5, 80/20 314-321, 60/30/10 318-320
         std::vector<uint32_t> sizes;
         if (so) {
             const std::vector<uint32_t>& pct = stream_split_;
@@ -1364,7 +1364,7 @@ private:
         size_t lc = (n + 1) / 2;
         size_t L = (size_t)ceil_log2(lc);
         size_t pad = lc + ((size_t)1 << L) + 8;  // slack for the +1 slots and the top levels
-        return n * 64 + 2 * lc * 64 + pad * 32 * (4 + 8 + 3 + 3) + lc * (sizeof(MergeDesc<FB>) + 32 + 32 * 3 / 2) + 4096;
+        return n * 64 + 2 * lc * 64 + pad * 32 * (4 + 8 + 2 + 3) + pad * 32 * (L + 1) + lc * (sizeof(MergeDesc<FB>) + 32 + 32 * 3 / 2) + 4096;
     }
 
     static F iso_gshift(uint32_t u) {   // (u^6 - 1) b
@@ -1458,7 +1458,12 @@ private:
         F* EB[2] = {(F*)eb_.ensure(std::max<size_t>(szE, 1) * 32), (F*)ob_.ensure(std::max<size_t>(szE, 1) * 32)};
         F* W[2] = {(F*)wk_[0].ensure(std::max<size_t>(szO, 1) * 32), (F*)wk_[1].ensure(std::max<size_t>(szO, 1) * 32)};
         F* TOP = (F*)top_.ensure(std::max<size_t>((size_t)nt * (L ? node_max[1] : 1), 1) * 32);
-        F* den = (F*)den_.ensure(std::max<size_t>(std::max(szO, (size_t)nt * node_max[0]), 1) * 32);
+        // 1 / ((x - alpha)(x - beta)) of every evaluation point of every level: the denominators depend on the point pyramid only, so
+        // the side stream computes and inverts them ahead of the polynomial levels (the latency-bound tails of 19 inversion batches and
+        // their serial base inversions leave the main stream)
+        std::vector<size_t> den_off(L + 1, 0);
+        for (int l = 0; l < L; ++l) den_off[l + 1] = den_off[l] + (((size_t)nt * node_max[l + 1]) << (l + 1));
+        F* den_all = (F*)den_.ensure(std::max<size_t>(den_off[L], 1) * 32);
         std::vector<size_t> desc_off(L + 1, 0);   // descriptors of every level are kept: the point pyramid runs ahead on its own stream
         for (int l = 0; l < L; ++l) desc_off[l + 1] = desc_off[l] + (size_t)nt * node_max[l + 1];
         MergeDesc<FB>* desc_all = (MergeDesc<FB>*)desc_.ensure(std::max<size_t>(desc_off[L], 1) * sizeof(MergeDesc<FB>));
@@ -1509,6 +1514,18 @@ private:
                     launch(k_merge_desc<FB>, wm, 128, (const Aff*)Pc, nodes, cnt_of(l), (const Aff*)Pp, merges, nt, desc_all + desc_off[l], iso_deg);
                 }
                 EAGEN_CUDA(cudaEventRecord(sync_event((size_t)l + 2), pst_));
+                // ... and straight away the inverse denominators of that merge (event L + 2 + l), so level l of the polynomial loop
+                // never waits for more of the pyramid than it needs
+                const int t = l + 1;
+                const double pts = present[l + 1] * (double)((size_t)1 << t);
+                prof_level_ = l;
+                {
+                    Scope ps(this, "merge_den", pts * 64.0, pts * 1.0);
+                    launch(k_den<FB>, wm << t, 256, (const MergeDesc<FB>*)(desc_all + desc_off[l]), wm, t, xtab(t), den_all + den_off[l], d_err_);
+                }
+                batch_invert(den_all + den_off[l], wm << t, pbinv_);
+                prof_level_ = -1;
+                EAGEN_CUDA(cudaEventRecord(sync_event((size_t)L + 2 + l), pst_));
             }
         }
         // level 0 on the main stream: the line functions of the leaves
@@ -1541,20 +1558,16 @@ private:
                 ntt(false, jf, 2, l, (size_t)nt * nodes, cnt_of(l), (int)nodes, (size_t)present[l], twist_tab(l), m);
             }
             // pointwise merge with exact division; parents' evaluations go to the next level's buffers (stride 2T)
-            EAGEN_CUDA(cudaStreamWaitEvent(st_, sync_event((size_t)l + 2), 0));   // this level's descriptors (side stream)
+            EAGEN_CUDA(cudaStreamWaitEvent(st_, sync_event((size_t)L + 2 + l), 0));   // this level's descriptors and inverse denominators (side stream)
             {
-                Scope ps(this, "merge_den", pts * 64.0, pts * 1.0);
-                launch(k_den<FB>, wm << t, 256, (const MergeDesc<FB>*)desc, wm, t, xtab(t), den, d_err_);
-            }
-            batch_invert(den, wm << t);
-            {
+                const F* den = den_all + den_off[l];
                 Scope ps(this, "merge_pointwise", pts * 288.0, pts * 11.0);
                 if (iso_u)
                     launch(k_pointwise<CC, true>, wm << t, 128, (const MergeDesc<FB>*)desc, wm, t, xtab(t), gtab(t), (const F*)EA[e], (const F*)EB[e],
-                           (const F*)den, merges, nodes, EA[e ^ 1], EB[e ^ 1], 2 * Tn, iso_gshift(iso_u));
+                           den, merges, nodes, EA[e ^ 1], EB[e ^ 1], 2 * Tn, iso_gshift(iso_u));
                 else
                     launch(k_pointwise<CC, false>, wm << t, 128, (const MergeDesc<FB>*)desc, wm, t, xtab(t), gtab(t), (const F*)EA[e], (const F*)EB[e],
-                           (const F*)den, merges, nodes, EA[e ^ 1], EB[e ^ 1], 2 * Tn, F::zero());
+                           den, merges, nodes, EA[e ^ 1], EB[e ^ 1], 2 * Tn, F::zero());
             }
             // back to coefficients (unscaled: stored = T * true), compact parent slots
             {
@@ -1614,11 +1627,8 @@ private:
         std::vector<int> htops((size_t)2 * nt);
         EAGEN_CUDA(cudaMemcpyAsync(htops.data(), tops, htops.size() * sizeof(int), cudaMemcpyDeviceToHost, st_));
         EAGEN_CUDA(cudaMemcpyAsync(roots, PT + pt_off[L], (size_t)nt * sizeof(Aff), cudaMemcpyDeviceToHost, st_));
-        for (int tr = 0; tr < nt; ++tr) {
-            size_t slot = first_slot + (dir > 0 ? (size_t)tr : (size_t)(nt - 1 - tr));
-            EAGEN_CUDA(cudaMemcpyAsync(res->A.as<F>() + slot * res->a_stride, A[cur] + (size_t)tr * ra, ra * 32, cudaMemcpyDeviceToDevice, st_));
-            EAGEN_CUDA(cudaMemcpyAsync(res->B.as<F>() + slot * res->b_stride, B[cur] + (size_t)tr * rb, rb * 32, cudaMemcpyDeviceToDevice, st_));
-        }
+        launch2d(k_copy_strided<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, (const F*)A[cur], ra, res->A.as<F>(), res->a_stride, (int)ra, first_slot, dir);
+        launch2d(k_copy_strided<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, (const F*)B[cur], rb, res->B.as<F>(), res->b_stride, (int)rb, first_slot, dir);
         int* herr = (int*)ring_.take(sizeof(int));
         EAGEN_CUDA(cudaMemcpyAsync(herr, d_err_, sizeof(int), cudaMemcpyDeviceToHost, st_));
         EAGEN_CUDA(cudaStreamSynchronize(st_));

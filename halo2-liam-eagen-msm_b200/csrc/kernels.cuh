@@ -1133,13 +1133,15 @@ __global__ void k_scale(Fe<FP>* __restrict__ coef, size_t stride, const int* __r
     stg(c, mul(ldg(c), ldg(linv + tree)));
 }
 
-// gather root functions of several trees into per-position result slots
+// root functions of the trees of a group into the result's slots: tree tr -> slot first_slot + (dir > 0 ? tr : ntrees - 1 - tr)
 template <class FP>
-__global__ void k_copy_strided(const Fe<FP>* __restrict__ src, size_t src_stride, Fe<FP>* __restrict__ dst, size_t dst_stride, int len) {
+__global__ void k_copy_strided(const Fe<FP>* __restrict__ src, size_t src_stride, Fe<FP>* __restrict__ dst, size_t dst_stride, int len,
+                               size_t first_slot, int dir) {
     int tree = blockIdx.y;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= len) return;
-    stg(dst + (size_t)tree * dst_stride + i, ldg(src + (size_t)tree * src_stride + i));
+    size_t slot = first_slot + (dir > 0 ? (size_t)tree : (size_t)(gridDim.y - 1 - tree));
+    stg(dst + slot * dst_stride + i, ldg(src + (size_t)tree * src_stride + i));
 }
 
 // pointwise product with scaling for the stand-alone polynomial product (Polynomial::mul_fft, :119-127)
