@@ -319,7 +319,12 @@ public:
         EAGEN_CUDA(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, dev_));
         EAGEN_CUDA(cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
         EAGEN_CUDA(cudaStreamCreateWithFlags(&cst_, cudaStreamNonBlocking));
-        EAGEN_CUDA(cudaStreamCreateWithFlags(&pst_, cudaStreamNonBlocking));
+        {   // the side stream produces what the main stream waits for (descriptors, inverse denominators): highest priority, so its
+            // blocks are placed as soon as SM resources free up instead of queueing behind the main stream's multi-millisecond grids
+            int lo = 0, hi = 0;
+            EAGEN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            EAGEN_CUDA(cudaStreamCreateWithPriority(&pst_, cudaStreamNonBlocking, hi));
+        }
         ls_ = st_;
         ring_.init((size_t)8 << 20);
         EAGEN_CUDA(cudaMalloc(&d_err_, sizeof(int)));
@@ -1188,6 +1193,7 @@ private:
             a.tw = tw(inverse, a.tw_t);
             a.twist = (p == 0) ? twist : nullptr;
             a.dst_off = dst_off;
+            a.final_pass = (p + 1 == plan.size()) ? 1 : 0;
             for (int j = 0; j < 2; ++j) {
                 const NttJob& jb = jobs[j < njobs ? j : 0];
                 NttSide<FB>& sd = a.side[j];
@@ -1241,7 +1247,10 @@ private:
             run_negbase(ds, n, prm, planes, rows);
             run_multiples(dp, n, (uint8_t)prm.base, tab);
         }
-        int per_thread = 32;
+        // points per thread: every block ends with a 7-step tree reduce of complete additions behind barriers, so large inputs
+        // amortise it over 128 points per thread (measured at 2^20 Pallas, tools/scope_ms.py: 32 -> 15.3 ms, 64 -> 13.5, 128 -> 12.6);
+        // smaller inputs keep 32 so that the grid still fills the chip
+        int per_thread = n >= ((size_t)1 << 19) ? 128 : 32;
         size_t chunk = (size_t)SUMS_THREADS * per_thread;
         int chunks = (int)std::max<size_t>(1, (n + chunk - 1) / chunk);
         Prj* partials = (Prj*)partials_.ensure((size_t)d * chunks * sizeof(Prj));
@@ -1532,14 +1541,12 @@ private:
         EAGEN_CUDA(cudaStreamWaitEvent(st_, sync_event(1), 0));
         {
             Scope ps(this, "pair_points", present[0] * (128.0 + 64.0 + 96.0), present[0] * 2.0);
-            launch(k_leaf_lines<FB>, w0, 256, T, cap, (const int*)dlv, (const Aff*)(PT + pt_off[0]), node_max[0], nt, A[0], B[0], iso_deg);
+            // ... and, with them, the leaves' evaluations on the 2-point domain (no separate 2-point transform)
+            launch(k_leaf_lines<FB>, w0, 256, T, cap, (const int*)dlv, (const Aff*)(PT + pt_off[0]), node_max[0], nt, A[0], B[0],
+                   L > 0 ? EA[0] : (F*)nullptr, L > 0 ? EB[0] : (F*)nullptr, iso_deg);
         }
 
         int cur = 0, e = 0;
-        if (L > 0) {  // the leaves' evaluations on the 2-point domain (full forward transform, true coefficients)
-            NttJob jl[2] = {{W[0], A[0], 2, 2, EA[0], 2, 2, nullptr}, {W[1], B[0], 1, 1, EB[0], 2, 2, nullptr}};
-            ntt(false, jl, 2, 1, (size_t)nt * node_max[0], cnt_of(0), (int)node_max[0], (size_t)present[0]);
-        }
         for (int l = 0; l < L; ++l) {
             prof_level_ = l;
             struct LevelReset { int& v; ~LevelReset() { v = -1; } } level_reset{prof_level_};
@@ -1620,15 +1627,19 @@ private:
             F* lead = (F*)lead_.ensure((size_t)std::max(nt, 1) * 32);
             launch(k_lead<FB>, nt, 64, (const F*)A[cur], ra, (const int*)tops, (const F*)B[cur], rb, (const int*)(tops + nt), nt, lead);
             batch_invert(lead, nt);
-            launch2d(k_scale<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, A[cur], ra, (const int*)tops, (const F*)lead);
-            launch2d(k_scale<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, B[cur], rb, (const int*)(tops + nt), (const F*)lead);
+            launch2d(k_scale<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, (const F*)A[cur], ra, (const int*)tops, (const F*)lead,
+                     res->A.as<F>(), res->a_stride, first_slot, dir);
+            launch2d(k_scale<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, (const F*)B[cur], rb, (const int*)(tops + nt), (const F*)lead,
+                     res->B.as<F>(), res->b_stride, first_slot, dir);
         }
         // scatter into the result slots
         std::vector<int> htops((size_t)2 * nt);
         EAGEN_CUDA(cudaMemcpyAsync(htops.data(), tops, htops.size() * sizeof(int), cudaMemcpyDeviceToHost, st_));
         EAGEN_CUDA(cudaMemcpyAsync(roots, PT + pt_off[L], (size_t)nt * sizeof(Aff), cudaMemcpyDeviceToHost, st_));
-        launch2d(k_copy_strided<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, (const F*)A[cur], ra, res->A.as<F>(), res->a_stride, (int)ra, first_slot, dir);
-        launch2d(k_copy_strided<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, (const F*)B[cur], rb, res->B.as<F>(), res->b_stride, (int)rb, first_slot, dir);
+        if (flags & EAGEN_RAW_TREE) {   // canonical form: k_scale has already written the slots
+            launch2d(k_copy_strided<FB>, dim3((unsigned)((ra + 255) / 256), nt), 256, (const F*)A[cur], ra, res->A.as<F>(), res->a_stride, (int)ra, first_slot, dir);
+            launch2d(k_copy_strided<FB>, dim3((unsigned)((rb + 255) / 256), nt), 256, (const F*)B[cur], rb, res->B.as<F>(), res->b_stride, (int)rb, first_slot, dir);
+        }
         int* herr = (int*)ring_.take(sizeof(int));
         EAGEN_CUDA(cudaMemcpyAsync(herr, d_err_, sizeof(int), cudaMemcpyDeviceToHost, st_));
         EAGEN_CUDA(cudaStreamSynchronize(st_));

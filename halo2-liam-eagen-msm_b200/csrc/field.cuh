@@ -390,6 +390,74 @@ EAGEN_HD Fe<FP> mul_chain(const Fe<FP>& a, const Fe<FP>& b) {
     return r;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Lazily reduced arithmetic for the transform's butterflies: values live in [0, 2p) between stages (2p < 2^256 for every modulus
+// here), twiddles stay canonical.  Congruent to the canonical operations mod p; normalise_lazy brings a value back to [0, p), so
+// a transform that normalises its outputs produces the same bits as one on canonical values.
+//   mul_lazy(a, w): a < 2p, w < p.  The interleaved reduction leaves T = (a w + M p) / R with M < R, so T < p (2p/R + 1) < 2p
+//                   because p < R/2: the final conditional subtraction of the canonical product is simply not needed.
+//   add_lazy / sub_lazy: one conditional correction by 2p (a + b may carry out of limb 7: 4p > 2^256 for the Pasta moduli).
+// ------------------------------------------------------------------------------------------------
+template <class FP>
+EAGEN_HD constexpr uint32_t mod2(int i) { return (FP::mod(i) << 1) | (i ? (FP::mod(i - 1) >> 31) : 0u); }   // limb i of 2p
+
+template <class FP>
+EAGEN_HD Fe<FP> mul_lazy(const Fe<FP>& a, const Fe<FP>& b) {
+    static_assert((FP::mod(7) >> 31) == 0, "lazy reduction assumes p < 2^255");
+#if defined(__CUDA_ARCH__)
+    uint32_t X[8], Y[8];
+    mont_row<FP, true>(X, Y, a.v, b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; i += 2) {
+        mont_row<FP, false>(Y, X, a.v, b.v[i]);
+        if (i + 1 < 8) mont_row<FP, false>(X, Y, a.v, b.v[i + 1]);
+    }
+    Fe<FP> r;
+    cc::add_cc(r.v[0], X[1], Y[0]);
+#pragma unroll
+    for (int k = 1; k < 7; ++k) cc::addc_cc(r.v[k], X[k + 1], Y[k]);
+    cc::addc(r.v[7], Y[7], 0);
+    return r;
+#else
+    return mul_portable(a, b);   // host: canonical result, a member of the same residue class below 2p
+#endif
+}
+template <class FP>
+EAGEN_HD Fe<FP> add_lazy(const Fe<FP>& a, const Fe<FP>& b) {
+    Fe<FP> r;
+    uint32_t c8, s[8], t;
+    cc::add_cc(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) cc::addc_cc(r.v[i], a.v[i], b.v[i]);
+    cc::addc(c8, 0, 0);                                   // bit 256 of a + b
+    cc::sub_cc(s[0], r.v[0], mod2<FP>(0));
+#pragma unroll
+    for (int i = 1; i < 8; ++i) cc::subc_cc(s[i], r.v[i], mod2<FP>(i));
+    cc::subc(t, c8, 0);                                   // c8 - borrow: all ones exactly when a + b < 2p
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.v[i] = (t >> 31) ? r.v[i] : s[i];
+    return r;
+}
+template <class FP>
+EAGEN_HD Fe<FP> sub_lazy(const Fe<FP>& a, const Fe<FP>& b) {
+    Fe<FP> r;
+    uint32_t mask;
+    cc::sub_cc(r.v[0], a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) cc::subc_cc(r.v[i], a.v[i], b.v[i]);
+    cc::subc(mask, 0, 0);   // all ones when a < b
+    cc::add_cc(r.v[0], r.v[0], mod2<FP>(0) & mask);
+#pragma unroll
+    for (int i = 1; i < 7; ++i) cc::addc_cc(r.v[i], r.v[i], mod2<FP>(i) & mask);
+    cc::addc(r.v[7], r.v[7], mod2<FP>(7) & mask);
+    return r;
+}
+template <class FP>
+EAGEN_HD Fe<FP> normalise_lazy(Fe<FP> a) {   // [0, 2p) -> [0, p)
+    reduce_once_cc<FP>(a.v);
+    return a;
+}
+
 template <class FP>
 EAGEN_HD Fe<FP> mul(const Fe<FP>& a, const Fe<FP>& b) {
 #if defined(__CUDA_ARCH__)

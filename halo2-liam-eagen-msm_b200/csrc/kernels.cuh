@@ -354,8 +354,11 @@ __global__ void k_jac_to_affine(const Fe<FP>* __restrict__ jac, const Fe<FP>* __
 // ------------------------------------------------------------------------------------------------
 constexpr int SUMS_THREADS = 128;
 
+#ifndef EAGEN_SUMS_MINBLOCKS
+#define EAGEN_SUMS_MINBLOCKS 5
+#endif
 template <class CC>
-__global__ void __launch_bounds__(SUMS_THREADS, 5)
+__global__ void __launch_bounds__(SUMS_THREADS, EAGEN_SUMS_MINBLOCKS)
 k_digit_sums(const uint8_t* __restrict__ planes, const Affine<typename CC::Base>* __restrict__ table, size_t n, uint32_t base,
              int per_thread, Proj<typename CC::Base>* __restrict__ partials /* d x chunks */) {
     typedef typename CC::Base F;
@@ -606,6 +609,7 @@ template <class FP>
 __global__ void k_leaf_lines(const Affine<FP>* __restrict__ T, size_t t_stride, const int* __restrict__ t_cnt,
                              const Affine<FP>* __restrict__ outp, size_t out_stride, int ntrees,
                              Fe<FP>* __restrict__ A /* stride 2 */, Fe<FP>* __restrict__ B /* stride 1 */,
+                             Fe<FP>* __restrict__ EA /* optional, stride 2 */, Fe<FP>* __restrict__ EB /* optional, stride 2 */,
                              int* __restrict__ iso_deg /* optional: per tree, += 5 for every leaf that is a line */) {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= out_stride * ntrees) return;
@@ -627,6 +631,10 @@ __global__ void k_leaf_lines(const Affine<FP>* __restrict__ T, size_t t_stride, 
     stg(A + 2 * g, lz);
     stg(A + 2 * g + 1, lx);
     stg(B + g, ly);
+    if (EA) {   // the leaf's values on the 2-point domain {1, -1} (what a 2-point forward transform of [lz, lx] and [ly] gives)
+        stg(EA + 2 * g, add(lz, lx)); stg(EA + 2 * g + 1, sub(lz, lx));
+        stg(EB + 2 * g, ly); stg(EB + 2 * g + 1, ly);
+    }
 }
 
 // per-merge descriptor for the level that joins children (2j, 2j+1)
@@ -699,6 +707,7 @@ struct NttPass {
     int node_max;            // transforms per tree (stride of the tree index)
     int t, s_hi, s_lo;
     int tw_t;                // log2 of the transform size the twiddle table `tw` belongs to (the contiguous pass uses the compact 2^k table)
+    int final_pass;          // last pass of the transform: stored values are normalised to [0, p)
 };
 
 EAGEN_D uint32_t insert_zero_bit(uint32_t v, int pos) {
@@ -743,8 +752,24 @@ EAGEN_D void ntt_sts(uint4* sm, uint32_t e, const Fe<FP>& r) {
 #endif
 #ifdef EAGEN_NTT_DIAG_NOMUL
 #define NTT_MUL(a, b) add(a, b)
-#else
+#elif defined(EAGEN_NTT_CANONICAL)   // round-1 butterflies on canonical values, kept for A/B timing (tools/variant.sh)
 #define NTT_MUL(a, b) mul(a, b)
+#define NTT_ADD(a, b) add(a, b)
+#define NTT_SUB(a, b) sub(a, b)
+#define NTT_NORM(a) (a)
+#else
+// Butterflies on lazily reduced values (field.cuh): everything in shared memory and between the passes of one transform lies in
+// [0, 2p); the product by a canonical twiddle needs no final subtraction.  The LAST pass normalises what it stores, so a
+// transform's outputs are canonical and bit-identical to the fully reduced formulation.
+#define NTT_MUL(a, b) mul_lazy(a, b)
+#define NTT_ADD(a, b) add_lazy(a, b)
+#define NTT_SUB(a, b) sub_lazy(a, b)
+#define NTT_NORM(a) normalise_lazy(a)
+#endif
+#ifdef EAGEN_NTT_DIAG_NOMUL
+#define NTT_ADD(a, b) add(a, b)
+#define NTT_SUB(a, b) sub(a, b)
+#define NTT_NORM(a) (a)
 #endif
 template <class FP, bool INVERSE>
 __global__ void __launch_bounds__(NTT_THREADS, EAGEN_NTT_MINBLOCKS)
@@ -788,7 +813,7 @@ k_ntt_pass(NttPass<FP> a) {
                 if (sd.src) {
                     if ((int)i < sd.src_len) {
                         v = ldg(sd.src + tr * sd.src_stride + i);
-                        if (a.twist) v = mul(v, ldg(a.twist + i));
+                        if (a.twist) v = NTT_MUL(v, ldg(a.twist + i));
                     }
                 }
                 else v = ldg(sd.data + lin[r]);
@@ -820,15 +845,15 @@ k_ntt_pass(NttPass<FP> a) {
             // round alone carries three quarters of them.  Multiplying by the Montgomery 1 would give the same bits.
             const Fe<FP> W1b = ldg(a.tw + NTT_TWI((size_t)1 << (a.tw_t - 2)));   // w_4 (or its inverse)
             if (INVERSE) {
-                Fe<FP> y0 = add(x0, x1), y1 = sub(x0, x1), y2 = add(x2, x3), y3 = sub(x2, x3);
+                Fe<FP> y0 = NTT_ADD(x0, x1), y1 = NTT_SUB(x0, x1), y2 = NTT_ADD(x2, x3), y3 = NTT_SUB(x2, x3);
                 Fe<FP> u3 = NTT_MUL(y3, W1b);
-                ntt_sts(sm, i0, add(y0, y2)); ntt_sts(sm, i0 + 2 * d, sub(y0, y2));
-                ntt_sts(sm, i0 + d, add(y1, u3)); ntt_sts(sm, i0 + 3 * d, sub(y1, u3));
+                ntt_sts(sm, i0, NTT_ADD(y0, y2)); ntt_sts(sm, i0 + 2 * d, NTT_SUB(y0, y2));
+                ntt_sts(sm, i0 + d, NTT_ADD(y1, u3)); ntt_sts(sm, i0 + 3 * d, NTT_SUB(y1, u3));
             } else {
-                Fe<FP> y0 = add(x0, x2), y2 = sub(x0, x2);
-                Fe<FP> y1 = add(x1, x3), y3 = NTT_MUL(sub(x1, x3), W1b);
-                ntt_sts(sm, i0, add(y0, y1)); ntt_sts(sm, i0 + d, sub(y0, y1));
-                ntt_sts(sm, i0 + 2 * d, add(y2, y3)); ntt_sts(sm, i0 + 3 * d, sub(y2, y3));
+                Fe<FP> y0 = NTT_ADD(x0, x2), y2 = NTT_SUB(x0, x2);
+                Fe<FP> y1 = NTT_ADD(x1, x3), y3 = NTT_MUL(NTT_SUB(x1, x3), W1b);
+                ntt_sts(sm, i0, NTT_ADD(y0, y1)); ntt_sts(sm, i0 + d, NTT_SUB(y0, y1));
+                ntt_sts(sm, i0 + 2 * d, NTT_ADD(y2, y3)); ntt_sts(sm, i0 + 3 * d, NTT_SUB(y2, y3));
             }
         } else {
             const Fe<FP> W0 = ldg(a.tw + NTT_TWI(jl << (a.tw_t - 1 - sgl)));
@@ -836,15 +861,15 @@ k_ntt_pass(NttPass<FP> a) {
             const Fe<FP> W1b = ldg(a.tw + NTT_TWI((jl + ((size_t)1 << sgl)) << (a.tw_t - 1 - sgh)));
             if (INVERSE) {   // decimation in time: stage slo (distance d), then stage slo+1 (distance 2d)
                 Fe<FP> v1 = NTT_MUL(x1, W0), v3 = NTT_MUL(x3, W0);
-                Fe<FP> y0 = add(x0, v1), y1 = sub(x0, v1), y2 = add(x2, v3), y3 = sub(x2, v3);
+                Fe<FP> y0 = NTT_ADD(x0, v1), y1 = NTT_SUB(x0, v1), y2 = NTT_ADD(x2, v3), y3 = NTT_SUB(x2, v3);
                 Fe<FP> u2 = NTT_MUL(y2, W1a), u3 = NTT_MUL(y3, W1b);
-                ntt_sts(sm, i0, add(y0, u2)); ntt_sts(sm, i0 + 2 * d, sub(y0, u2));
-                ntt_sts(sm, i0 + d, add(y1, u3)); ntt_sts(sm, i0 + 3 * d, sub(y1, u3));
+                ntt_sts(sm, i0, NTT_ADD(y0, u2)); ntt_sts(sm, i0 + 2 * d, NTT_SUB(y0, u2));
+                ntt_sts(sm, i0 + d, NTT_ADD(y1, u3)); ntt_sts(sm, i0 + 3 * d, NTT_SUB(y1, u3));
             } else {         // decimation in frequency: stage slo+1 (distance 2d), then stage slo (distance d)
-                Fe<FP> y0 = add(x0, x2), y2 = NTT_MUL(sub(x0, x2), W1a);
-                Fe<FP> y1 = add(x1, x3), y3 = NTT_MUL(sub(x1, x3), W1b);
-                ntt_sts(sm, i0, add(y0, y1)); ntt_sts(sm, i0 + d, NTT_MUL(sub(y0, y1), W0));
-                ntt_sts(sm, i0 + 2 * d, add(y2, y3)); ntt_sts(sm, i0 + 3 * d, NTT_MUL(sub(y2, y3), W0));
+                Fe<FP> y0 = NTT_ADD(x0, x2), y2 = NTT_MUL(NTT_SUB(x0, x2), W1a);
+                Fe<FP> y1 = NTT_ADD(x1, x3), y3 = NTT_MUL(NTT_SUB(x1, x3), W1b);
+                ntt_sts(sm, i0, NTT_ADD(y0, y1)); ntt_sts(sm, i0 + d, NTT_MUL(NTT_SUB(y0, y1), W0));
+                ntt_sts(sm, i0 + 2 * d, NTT_ADD(y2, y3)); ntt_sts(sm, i0 + 3 * d, NTT_MUL(NTT_SUB(y2, y3), W0));
             }
         }
         __syncthreads();
@@ -863,18 +888,18 @@ k_ntt_pass(NttPass<FP> a) {
             size_t j = ((size_t)(E & ((1u << sigma) - 1)) << a.s_lo) | L;
             Fe<FP> u = ntt_lds<FP>(sm, i0), v = ntt_lds<FP>(sm, i1);
             if (sg == 0) {   // w = 1 for every butterfly of global stage 0
-                ntt_sts(sm, i0, add(u, v));
-                ntt_sts(sm, i1, sub(u, v));
+                ntt_sts(sm, i0, NTT_ADD(u, v));
+                ntt_sts(sm, i1, NTT_SUB(u, v));
                 continue;
             }
             Fe<FP> wj = ldg(a.tw + NTT_TWI(j << (a.tw_t - 1 - sg)));
             if (INVERSE) {
                 v = NTT_MUL(v, wj);
-                ntt_sts(sm, i0, add(u, v));
-                ntt_sts(sm, i1, sub(u, v));
+                ntt_sts(sm, i0, NTT_ADD(u, v));
+                ntt_sts(sm, i1, NTT_SUB(u, v));
             } else {
-                ntt_sts(sm, i0, add(u, v));
-                ntt_sts(sm, i1, NTT_MUL(sub(u, v), wj));
+                ntt_sts(sm, i0, NTT_ADD(u, v));
+                ntt_sts(sm, i1, NTT_MUL(NTT_SUB(u, v), wj));
             }
         }
         __syncthreads();
@@ -888,6 +913,7 @@ k_ntt_pass(NttPass<FP> a) {
         if (a.s_lo == 0) { E = q & ((1u << k) - 1); wl = q >> k; }
         else { wl = q & ((1u << lw) - 1); E = q >> lw; }
         Fe<FP> v = ntt_lds<FP>(sm, (E << lw) | wl);
+        if (a.final_pass) v = NTT_NORM(v);   // the transform's outputs leave canonical
         if (sd.dst) {
             size_t tr = lin[r] >> a.t, i = lin[r] & Tmask;
             if ((int)i < sd.dst_len) {
@@ -1124,13 +1150,15 @@ __global__ void k_lead(const Fe<FP>* __restrict__ A, size_t sa, const int* __res
     stg(lead + tree, l);
 }
 
+// monic scaling of the root functions, written straight into the result's slots (tree tr -> slot first_slot + (dir > 0 ? tr : ntrees-1-tr))
 template <class FP>
-__global__ void k_scale(Fe<FP>* __restrict__ coef, size_t stride, const int* __restrict__ top, const Fe<FP>* __restrict__ linv) {
+__global__ void k_scale(const Fe<FP>* __restrict__ coef, size_t stride, const int* __restrict__ top, const Fe<FP>* __restrict__ linv,
+                        Fe<FP>* __restrict__ dst, size_t dst_stride, size_t first_slot, int dir) {
     int tree = blockIdx.y;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= top[tree]) return;
-    Fe<FP>* c = coef + (size_t)tree * stride + i;
-    stg(c, mul(ldg(c), ldg(linv + tree)));
+    size_t slot = first_slot + (dir > 0 ? (size_t)tree : (size_t)(gridDim.y - 1 - tree));
+    stg(dst + slot * dst_stride + i, mul(ldg(coef + (size_t)tree * stride + i), ldg(linv + tree)));
 }
 
 // root functions of the trees of a group into the result's slots: tree tr -> slot first_slot + (dir > 0 ? tr : ntrees - 1 - tr)
