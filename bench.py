@@ -51,14 +51,14 @@ def peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region"""
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index, period_ms=500):
+        self.index, self.proc, self.lines, self.period_ms = index, None, [], period_ms
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "500"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -173,6 +173,7 @@ def main():
                     help="BASELINE config 4 is --curve vesta --log-n 21 under torchrun with 8 ranks (2^24 points)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, what the driver runs): 2^log_n points per GPU; strong: 2^log_n points in TOTAL, 2^log_n / N per GPU")
+    ap.add_argument("--clock-period-ms", type=int, default=500, help="nvidia-smi polling period during the timed region (0: no sampling; diagnostic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -232,9 +233,9 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     ctx.profile_reset()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, args.clock_period_ms)
     barrier()
-    if rank == 0:
+    if rank == 0 and args.clock_period_ms > 0:
         sampler.start()
     l0 = ctx.launch_count()
     t0 = time.perf_counter()

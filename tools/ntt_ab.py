@@ -4,7 +4,9 @@ import os, sys, subprocess, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if len(sys.argv) > 1 and sys.argv[1] != "--child":
     for lib in sys.argv[1:]:
-        subprocess.run(["cp", lib, os.path.join(ROOT, "halo2-liam-eagen-msm_b200", "libeagen_msm.so")], check=True)
+        dst = os.path.join(ROOT, "halo2-liam-eagen-msm_b200", "libeagen_msm.so")
+        if os.path.abspath(lib) != os.path.abspath(dst):
+            subprocess.run(["cp", lib, dst], check=True)
         out = subprocess.run([sys.executable, __file__, "--child"], capture_output=True, text=True)
         print(lib, out.stdout.strip(), out.stderr.strip()[-300:])
     sys.exit(0)

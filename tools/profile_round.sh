@@ -18,9 +18,14 @@ $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
 # one witness step has ~60 NTT launches, 19 pointwise, ~110 binv_down: skip the warm-up step and the small bottom levels
 ncu --set full --clock-control none --import-source on -k regex:'k_ntt_pass|k_pointwise|k_binv_down|k_binv_up' -s 290 -c 14 \
     -o /tmp/${TAG}_full_ntt_pw $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'k_negbase|k_digit_sums|k_den|k_fixup|k_merge_desc|k_pair_finish|k_binv_base|k_scatter_points' -s 40 -c 10 \
+# the small kernels, each family at the launches of the SECOND step (the first step of one_step.py is the warm-up)
+ncu --set full --clock-control none --import-source on -k regex:'k_negbase|k_digit_sums|k_scatter_points|k_multiples_proj' -s 4 -c 4 \
     -o /tmp/${TAG}_full_small $CMD > gpurun_out/${TAG}_ncu3.log 2>&1
-for r in ntt_pw small; do
+ncu --set full --clock-control none --import-source on -k regex:'k_den|k_fixup' -s 40 -c 6 \
+    -o /tmp/${TAG}_full_den_fixup $CMD > gpurun_out/${TAG}_ncu4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_merge_desc|k_pair_finish|k_pair_den|k_leaf_lines|k_binv_base' -s 78 -c 6 \
+    -o /tmp/${TAG}_full_pyramid $CMD > gpurun_out/${TAG}_ncu5.log 2>&1
+for r in ntt_pw small den_fixup pyramid; do
   ncu -i /tmp/${TAG}_full_${r}.ncu-rep --page raw --csv > gpurun_out/${TAG}_full_${r}_raw.csv 2>/dev/null
 done
 echo profile_round done
