@@ -60,7 +60,10 @@ enum : int {
 // ------------------------------------------------------------------------------------------------
 // K9  batched inversion (Montgomery trick), hierarchical: each thread owns G strided elements
 // ------------------------------------------------------------------------------------------------
-constexpr int BINV_G = 16;
+#ifndef EAGEN_BINV_G
+#define EAGEN_BINV_G 16
+#endif
+constexpr int BINV_G = EAGEN_BINV_G;
 
 template <class FP>
 __global__ void k_binv_up(const Fe<FP>* __restrict__ x, Fe<FP>* __restrict__ pref, Fe<FP>* __restrict__ tot, size_t M, size_t Tn) {

@@ -43,6 +43,17 @@ pub fn check(ctx: *mut eagen_ctx, rc: i32) {
     }
 }
 
+// The marshalling below reinterprets field elements as `[u64; 4]`: checked at compile time for the instantiated fields (a field
+// type of another size or alignment fails the build instead of corrupting memory).  Whether the four words ARE the Montgomery
+// residue is a property of halo2curves / pasta_curves that the reference itself relies on (`from_raw_bytes_unchecked`,
+// reference: src/precomputed_fft_data.rs:72); pin it with one vector produced by the real crate once a toolchain exists.
+const _: () = {
+    assert!(std::mem::size_of::<halo2curves::pasta::Fp>() == 32 && std::mem::align_of::<halo2curves::pasta::Fp>() <= 8);
+    assert!(std::mem::size_of::<halo2curves::pasta::Fq>() == 32 && std::mem::align_of::<halo2curves::pasta::Fq>() <= 8);
+    assert!(std::mem::size_of::<halo2curves::bn256::Fr>() == 32 && std::mem::align_of::<halo2curves::bn256::Fr>() <= 8);
+    assert!(std::mem::size_of::<halo2curves::bn256::Fq>() == 32 && std::mem::align_of::<halo2curves::bn256::Fq>() <= 8);
+};
+
 /// Montgomery limbs of a field element: both halo2curves and pasta_curves store `[u64; 4]` Montgomery residues and
 /// the reference itself reinterprets raw bytes that way (reference: src/precomputed_fft_data.rs:72).
 pub fn felt_to_limbs<F: PrimeField>(x: &F) -> [u64; 4] {

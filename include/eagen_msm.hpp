@@ -251,5 +251,38 @@ inline LhsWitness compute_lhs_witness(const Context& ctx, const std::vector<Felt
     return w;
 }
 
+// The same call over several GPUs: every rank passes its contiguous share of the points and gets the functions
+// of its share of the digit positions; `first_function` is the index k of functions[0] in the whole witness.  The communicator comes
+// from join() (multi-process: the 128-byte id of unique_id() reaches the other ranks over any side channel) or from
+// eagen_comm_init_all (one process, one thread per context).
+struct ShardedLhsWitness {
+    AffinePoint carry;                                              // sum over ALL ranks' points (the same on every rank)
+    size_t first_function = 0;
+    std::vector<regular_functions_utils::RegularFunction> functions;
+};
+inline std::array<unsigned char, EAGEN_COMM_ID_BYTES> unique_id() {
+    std::array<unsigned char, EAGEN_COMM_ID_BYTES> id{};
+    int rc = eagen_comm_unique_id(id.data());
+    if (rc != EAGEN_OK) throw Error(rc, eagen_last_error(nullptr));
+    return id;
+}
+inline void join(const Context& ctx, int nranks, int rank, const std::array<unsigned char, EAGEN_COMM_ID_BYTES>& id) {
+    ctx.check(eagen_comm_init(ctx.raw(), nranks, rank, id.data()));
+}
+inline ShardedLhsWitness compute_lhs_witness_sharded(const Context& ctx, const std::vector<Felt>& my_scalars, const std::vector<JacobianPoint>& my_pts,
+                                                     uint8_t base, uint32_t flags = EAGEN_CANONICAL) {
+    if (my_scalars.size() != my_pts.size()) throw Error(EAGEN_E_LEN, "incompatible amount of coefficients");
+    eagen_result* r = nullptr;
+    ctx.check(eagen_lhs_witness_sharded(ctx.raw(), my_scalars.empty() ? nullptr : my_scalars[0].data(), my_pts.empty() ? nullptr : my_pts[0].data(),
+                                        my_pts.size(), base, flags, nullptr, 0, &r));
+    ShardedLhsWitness w;
+    eagen_result_carry(r, w.carry.data());
+    w.first_function = eagen_result_first_function(r);
+    size_t nf = eagen_result_num_functions(r);
+    for (size_t k = 0; k < nf; ++k) w.functions.push_back(regular_functions_utils::function_from_result(r, k));
+    eagen_result_free(r);
+    return w;
+}
+
 }  // namespace argument_witness_calc
 }  // namespace eagen
