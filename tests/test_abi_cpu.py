@@ -226,3 +226,58 @@ def test_pasta_fft_precomp_matches_published_root_of_unity(eagen, oracle):
             wi = oracle.unpack_felts(eagen.omega_pow_inv(cv.id, k), p)[0]
             h = oracle.unpack_felts(eagen.half_pow(cv.id, k), p)[0]
             assert w == pow(root, 1 << min(k, 40), p) and w * wi % p == 1 and h * pow(2, k, p) % p == 1
+
+
+def test_fft_precomp_large_exponents_terminate(eagen):
+    """half_pow(exp) must be square-and-multiply (a 2^60 exponent returns at once) and omega_pow(k) is the identity from
+    k = S on instead of silently clamping"""
+    cv = pyref.Curve("pallas")
+    h = eagen.half_pow(eagen.PALLAS, (1 << 60) + 12345)
+    want = pow(pow(2, -1, cv.p), (1 << 60) + 12345, cv.p)
+    import oracle_lib
+    assert oracle_lib.unpack_felts(h, cv.p)[0] == want
+    one = oracle_lib.pack_felts([1], cv.p)[0]
+    for k in (32, 33, 1000, (1 << 40)):
+        assert (eagen.omega_pow(eagen.PALLAS, k) == one).all()
+        assert (eagen.omega_pow_inv(eagen.PALLAS, k) == one).all()
+
+
+def test_sharding_plan_entry_points_need_no_device(eagen):
+    """eagen_position_range / eagen_lhs_witness_sharded_layout are pure host arithmetic: the d positions are partitioned into
+    contiguous, balanced ranges, and a rank's streamed buffer holds exactly its positions' slots"""
+    for d in (33, 56, 65, 129):
+        for world in (1, 2, 3, 4, 8):
+            rs = [eagen.position_range(r, world, d) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == d and all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+            assert max(b - a for a, b in rs) - min(b - a for a, b in rs) <= 1
+    with pytest.raises(eagen.EagenError):
+        eagen.position_range(8, 8, 56)
+    L = eagen.lib()
+    d = eagen.num_digits(eagen.PALLAS, 5)
+    a, b, tot = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    whole = 0
+    for r in range(8):
+        assert L.eagen_lhs_witness_sharded_layout(eagen.PALLAS, 1 << 20, C.c_uint8(5), r, 8, C.byref(a), C.byref(b), C.byref(tot)) == 0
+        lo, hi = eagen.position_range(r, 8, d)
+        assert tot.value == (hi - lo) * (a.value + b.value) * 32
+        whole += tot.value
+    a1, b1, t1 = C.c_size_t(), C.c_size_t(), C.c_size_t()
+    assert L.eagen_lhs_witness_stream_layout(eagen.PALLAS, 1 << 20, C.c_uint8(5), C.byref(a1), C.byref(b1), C.byref(t1)) == 0
+    assert (a1.value, b1.value) == (a.value, b.value) and t1.value == whole
+
+
+def test_oracle_synthetic_inputs_are_valid(oracle):
+    """the CPU restatement of the synthetic inputs (the golden hashes' inputs): scalars below isqrt(order)+2, points on the curve,
+    pairwise distinct, a function of the seed only"""
+    for name in ("pallas", "vesta", "grumpkin"):
+        cv = pyref.Curve(name)
+        S, P = oracle.synth_inputs(cv.id, 0xEA6E0002, 64)
+        S2, P2 = oracle.synth_inputs(cv.id, 0xEA6E0002, 32)
+        assert (S[:32] == S2).all() and (P[:32] == P2).all()
+        import math
+        lim = math.isqrt(cv.q) + 2
+        assert all(s < lim for s in oracle.unpack_felts(S, cv.q))
+        pts = oracle.unpack_affine(P[:, :8], cv.p)
+        assert len(set(pts)) == 64
+        for x, y in pts:
+            assert (y * y - x * x * x - cv.b) % cv.p == 0
