@@ -292,8 +292,9 @@ def main():
     # Scopes issued to the side stream (the point pyramid, "name~side") overlap the main stream's kernels: their event times are
     # not additive, so shares are taken over the main-stream scopes and the side-stream time is reported separately.
     hbm_peak, peak_src = peaks()
-    main = [e for e in prof if not e["kernel"].endswith("~side")]
+    main = [e for e in prof if "~" not in e["kernel"]]
     side_ms = sum(e["ms"] for e in prof if e["kernel"].endswith("~side"))
+    idle_ms = sum(e["ms"] for e in prof if e["kernel"] == "idle~gaps")
     tot_ms = sum(e["ms"] for e in main) or 1.0
     shares = {e["kernel"]: round(e["ms"] / tot_ms, 4) for e in sorted(main, key=lambda e: -e["ms"])}
     # the forward (coset) and inverse transforms are the same kernel template, k_ntt_pass: one group for the roofline
@@ -337,6 +338,7 @@ def main():
                     "imad_wide_per_s_measured": wide_peak, "imad32_per_s_measured": imad_peak, "imad_wide_per_modmul": 87,
                     "modmul_per_point": modmul_total / args.steps / n_total,
                     "side_stream_scope_ms_per_step": side_ms / args.steps,
+                    "main_stream_idle_between_scopes_ms_per_step": idle_ms / args.steps,
                     "note": "whole-step figure divides ALL counted products by the step time (device events around the call)"}
 
     cpu = None

@@ -9,6 +9,7 @@
 //   T_i --K5--> leaves --[K5 pair sums, K6 NTT, K7 merge, K9 inversions] x levels--> root (a, b) --K10--> canonical
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <memory>
 #include <mutex>
 #include <cstdio>
@@ -1027,10 +1028,29 @@ private:
         }
         size_t idx = 0;
     };
+    // host-side milliseconds spent while the GPU waits for the host (booked as "host~<what>"; profiling only)
+    void prof_host(const char* what, std::chrono::steady_clock::time_point t0) {
+        if (!prof_on_) return;
+        int t = prof_tag(what);
+        prof_[t].ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        prof_[t].scopes += 1;
+    }
     void prof_collect() {
         if (pending_.empty()) return;
         cudaStreamSynchronize(st_);
         cudaStreamSynchronize(pst_);
+        // idle time of the main stream between consecutive scopes (waits for the side stream, launch gaps): booked as "idle~gaps"
+        // (mode 2: one entry per scope that FOLLOWS the gap, "idle~before:<scope>")
+        const ProfPending* prev = nullptr;
+        std::vector<std::pair<std::string, double>> gaps;
+        for (auto& p : pending_) {
+            if (p.st != st_) continue;
+            float g = 0;
+            if (prev && cudaEventElapsedTime(&g, prev->b, p.a) == cudaSuccess && g > 0)
+                gaps.push_back({prof_detail_ ? "idle~before:" + prof_[p.tag].name : std::string("idle~gaps"), (double)g});
+            prev = &p;
+        }
+        for (auto& g : gaps) { int t = prof_tag(g.first.c_str()); prof_[t].ms += g.second; prof_[t].scopes += 1; }
         for (auto& p : pending_) {
             float ms = 0;
             if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) prof_[p.tag].ms += ms;
@@ -1059,11 +1079,14 @@ private:
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     int* d_err_ = nullptr;
     int last_tree_err_ = 0;
+    uint32_t plan_group_ = 0, plan_npos_ = 0;    // group plan of the last call that had to ask the driver for the free memory
+    size_t plan_per_tree_ = 0;
     ncclComm_t comm_ = nullptr;                  // multi-GPU: this rank's communicator (null: single GPU)
     int nranks_ = 1, rank_ = 0;
     bool comm_owned_ = false;
     cudaStream_t nst_ = nullptr;                 // communication stream (collectives overlap the carry chain)
     std::vector<uint32_t> stream_split_{75, 25}; // streamed output: per cent of the positions per group (eagen_ctx_set_stream_split)
+    std::vector<uint32_t> resident_split_{100};  // device-resident results: groups of positions (one group unless measured otherwise)
     DevBuf sh_planes_, sh_table_;
     void ensure_comm_stream() { if (!nst_) { use(); EAGEN_CUDA(cudaStreamCreateWithFlags(&nst_, cudaStreamNonBlocking)); } }
     PinnedRing ring_;
@@ -1293,6 +1316,7 @@ private:
         EAGEN_CUDA(cudaMemcpyAsync(hstage, tree_n, (size_t)d * sizeof(int), cudaMemcpyDeviceToHost, st_));
         EAGEN_CUDA(cudaMemcpyAsync(hstage + d, d_err_, sizeof(int), cudaMemcpyDeviceToHost, st_));
         EAGEN_CUDA(cudaStreamSynchronize(st_));
+        auto t_host = std::chrono::steady_clock::now();
         if (hstage[d] & (KERR_RANGE | KERR_DIGITS)) sync_check();   // throws with the proper status
         std::vector<int> hn(hstage, hstage + d);
         size_t nmax = 1;
@@ -1305,19 +1329,38 @@ private:
         res->alloc(res->A, res->nf * res->a_stride * 32);
         res->alloc(res->B, res->nf * res->b_stride * 32);
         res->la.assign(npos, 0); res->lb.assign(npos, 0);
-        // group positions so that one group's working set fits the memory budget
-        size_t free_b = 0, total_b = 0;
-        EAGEN_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        prof_host("host~result_alloc", t_host);
+        t_host = std::chrono::steady_clock::now();
+        // group positions so that one group's working set fits the memory budget.  cudaMemGetInfo was measured at 0.2 - 27 ms per call
+        // on the B200 boxes once the process holds tens of GB (it sits between two kernels with the GPU idle, and was the whole
+        // process-to-process spread of the step time: profiles/r02_experiments.md), so the plan of the previous call is reused
+        // whenever this call needs no more than that one did: the working buffers are grow-only and already large enough.
         size_t per_tree = tree_bytes(nmax);
-        size_t budget = (size_t)((double)(free_b + pooled_bytes()) * 0.80);
-        uint32_t group = (uint32_t)std::max<size_t>(1, std::min<size_t>(npos, budget / std::max<size_t>(per_tree, 1)));
+        uint32_t group;
+        if (plan_group_ && per_tree <= plan_per_tree_ && npos <= plan_npos_) {
+            group = std::min<uint32_t>(npos, plan_group_);
+        } else {
+            size_t free_b = 0, total_b = 0;
+            EAGEN_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            size_t budget = (size_t)((double)(free_b + pooled_bytes()) * 0.80);
+            group = (uint32_t)std::max<size_t>(1, std::min<size_t>(npos, budget / std::max<size_t>(per_tree, 1)));
+            plan_group_ = group; plan_per_tree_ = per_tree; plan_npos_ = npos;
+        }
+        prof_host("host~group_plan", t_host);
         // group sizes: as large as the memory budget allows; for streamed output a decreasing schedule (per cent of the positions,
         // eagen_ctx_set_stream_split, default 75,25) so that every group's copy hides behind the next group's compute and only the
         // small last group's copy is exposed.  More, smaller groups shorten the exposed copy but add ~1300 launches each:
         // measured (tools/e2e_groups.py, 2^20 Pallas, ms end to end): one group 328, 70/30 316, 75/25 315.5, 80/20 314-321, 60/30/10 318-320
         std::vector<uint32_t> sizes;
-        if (so) {
-            const std::vector<uint32_t>& pct = stream_split_;
+        std::vector<uint32_t> resident_pct = resident_split_;
+#ifdef EAGEN_DIAG_TUNE   // development builds only (tools/variant.sh -DEAGEN_DIAG_TUNE): never shipped
+        if (const char* e = getenv("EAGEN_DIAG_RESIDENT_SPLIT")) {
+            resident_pct.clear();
+            for (const char* q = e; *q;) { resident_pct.push_back((uint32_t)atoi(q)); while (*q && *q != ',') ++q; if (*q) ++q; }
+        }
+#endif
+        if (so || (resident_pct.size() > 1 && npos >= 8)) {
+            const std::vector<uint32_t>& pct = so ? stream_split_ : resident_pct;
             uint32_t left = npos;
             for (size_t i = 0; i < pct.size() && left; ++i) {
                 uint32_t want = i + 1 == pct.size() ? left : std::min<uint32_t>(left, std::max<uint32_t>(1, (npos * pct[i] + 50) / 100));
