@@ -447,10 +447,12 @@ public:
         run_shard_sums((const Fe<FS>*)d_scalars, (const F*)d_pts, n, prm, planes, rows, tab, sums);
         run_carry_chain(sums, 1, d, base, carries);
         res->carries.assign((size_t)d * 8, 0);
-        EAGEN_CUDA(cudaMemcpyAsync(res->carries.data(), carries, (size_t)d * 64, cudaMemcpyDeviceToHost, st_));
+        uint64_t* hcar = (uint64_t*)ring_.take((size_t)d * 64);   // pinned staging: a copy into pageable memory would block the host here
+        EAGEN_CUDA(cudaMemcpyAsync(hcar, carries, (size_t)d * 64, cudaMemcpyDeviceToHost, st_));
         if (!(flags & EAGEN_NO_FUNCTIONS)) run_position_trees(planes, tab, carries, n, base, d, 0, d, flags, res.get(), so);
         EAGEN_CUDA(cudaEventRecord(ev1_, st_));
         sync_check();
+        std::memcpy(res->carries.data(), hcar, (size_t)d * 64);
         std::memcpy(res->carry, &res->carries[(size_t)(d - 1) * 8], 64);
         float ms = 0; EAGEN_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
         res->device_ms = ms;
@@ -1086,7 +1088,6 @@ private:
     bool comm_owned_ = false;
     cudaStream_t nst_ = nullptr;                 // communication stream (collectives overlap the carry chain)
     std::vector<uint32_t> stream_split_{75, 25}; // streamed output: per cent of the positions per group (eagen_ctx_set_stream_split)
-    std::vector<uint32_t> resident_split_{100};  // device-resident results: groups of positions (one group unless measured otherwise)
     DevBuf sh_planes_, sh_table_;
     void ensure_comm_stream() { if (!nst_) { use(); EAGEN_CUDA(cudaStreamCreateWithFlags(&nst_, cudaStreamNonBlocking)); } }
     PinnedRing ring_;
@@ -1350,17 +1351,11 @@ private:
         // group sizes: as large as the memory budget allows; for streamed output a decreasing schedule (per cent of the positions,
         // eagen_ctx_set_stream_split, default 75,25) so that every group's copy hides behind the next group's compute and only the
         // small last group's copy is exposed.  More, smaller groups shorten the exposed copy but add ~1300 launches each:
-        // measured (tools/e2e_groups.py, 2^20 Pallas, ms end to end): one group 328, 70/30 316, 75/25 315.5, 80/20 314-321, 60/30/10 318-320
+        // measured (tools/e2e_groups.py, 2^20 Pallas, ms end to end): one group 328, 70/30 316, 75/25 315.5, 80/20 314-321, 60/30/10 318-320;
+        // device-resident results use one group per memory budget (two or more groups measured 289 / 292 / 295 ms against 286.5)
         std::vector<uint32_t> sizes;
-        std::vector<uint32_t> resident_pct = resident_split_;
-#ifdef EAGEN_DIAG_TUNE   // development builds only (tools/variant.sh -DEAGEN_DIAG_TUNE): never shipped
-        if (const char* e = getenv("EAGEN_DIAG_RESIDENT_SPLIT")) {
-            resident_pct.clear();
-            for (const char* q = e; *q;) { resident_pct.push_back((uint32_t)atoi(q)); while (*q && *q != ',') ++q; if (*q) ++q; }
-        }
-#endif
-        if (so || (resident_pct.size() > 1 && npos >= 8)) {
-            const std::vector<uint32_t>& pct = so ? stream_split_ : resident_pct;
+        if (so) {
+            const std::vector<uint32_t>& pct = stream_split_;
             uint32_t left = npos;
             for (size_t i = 0; i < pct.size() && left; ++i) {
                 uint32_t want = i + 1 == pct.size() ? left : std::min<uint32_t>(left, std::max<uint32_t>(1, (npos * pct[i] + 50) / 100));
