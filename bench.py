@@ -134,7 +134,7 @@ def run_reference(args):
     t_probe = oracle_sample_step(oracle_lib, (S, P), probe_n)
     log_n = args.ref_log_n
     def est(ln):
-        return t_probe * (1 << (ln - probe_n)) * (ln / float(probe_n)) ** 2 * 0.35   # threads are used better on larger trees
+        return t_probe * (1 << (ln - probe_n)) * (ln / float(probe_n)) ** 2 * 0.6    # calibrated on the 16-core GPU box: 2^12 in 1.5 s, 2^16 in 26 s
     while log_n > probe_n and est(log_n) * max(args.steps, 1) > args.ref_budget_s:
         log_n -= 1
     for _ in range(args.warmup):
@@ -167,7 +167,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--log-n", type=int, default=20, help="points per GPU = 2^log_n")
     ap.add_argument("--ref-log-n", type=int, default=16, help="points per CPU reference step: BASELINE config 2 (about 35 s per step on 16 cores)")
-    ap.add_argument("--ref-budget-s", type=float, default=400.0, help="the reference arm shrinks its step until K steps fit this many seconds")
+    ap.add_argument("--ref-budget-s", type=float, default=600.0, help="the reference arm shrinks its step until K steps fit this many seconds")
     ap.add_argument("--cpu-log-n", type=int, default=14, help="points of the cpu_baseline sample (about 12 s on 16 cores)")
     ap.add_argument("--curve", default="pallas", choices=["pallas", "vesta", "grumpkin"],
                     help="BASELINE config 4 is --curve vesta --log-n 21 under torchrun with 8 ranks (2^24 points)")
