@@ -623,6 +623,12 @@ template <class FP> void st_field(int op, const uint64_t* a, const uint64_t* b, 
         case 4: r = from_canonical(x); break;
         case 5: r = to_canonical(x); break;
         case 6: r = mul_chain(x, y); break;  // the device algorithm with a host-emulated carry flag
+        // lazily reduced arithmetic of the transform (operands in [0, 2p), twiddle y < p for the product); results are returned as
+        // they are, i.e. in [0, 2p), except op 10
+        case 7: r = mul_lazy(x, y); break;
+        case 8: r = add_lazy(x, y); break;
+        case 9: r = sub_lazy(x, y); break;
+        case 10: r = normalise_lazy(x); break;
         default: throw StatusError{EAGEN_E_ARG, "bad op"};
     }
     std::memcpy(out, r.v, 32);

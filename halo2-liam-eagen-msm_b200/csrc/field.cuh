@@ -404,8 +404,7 @@ EAGEN_HD constexpr uint32_t mod2(int i) { return (FP::mod(i) << 1) | (i ? (FP::m
 template <class FP>
 EAGEN_HD Fe<FP> mul_lazy(const Fe<FP>& a, const Fe<FP>& b) {
     static_assert((FP::mod(7) >> 31) == 0, "lazy reduction assumes p < 2^255");
-#if defined(__CUDA_ARCH__)
-    uint32_t X[8], Y[8];
+    uint32_t X[8], Y[8];   // the same chains on the host (emulated carry flag), so the CPU suite runs this very algorithm
     mont_row<FP, true>(X, Y, a.v, b.v[0]);
 #pragma unroll
     for (int i = 1; i < 8; i += 2) {
@@ -418,9 +417,6 @@ EAGEN_HD Fe<FP> mul_lazy(const Fe<FP>& a, const Fe<FP>& b) {
     for (int k = 1; k < 7; ++k) cc::addc_cc(r.v[k], X[k + 1], Y[k]);
     cc::addc(r.v[7], Y[7], 0);
     return r;
-#else
-    return mul_portable(a, b);   // host: canonical result, a member of the same residue class below 2p
-#endif
 }
 template <class FP>
 EAGEN_HD Fe<FP> add_lazy(const Fe<FP>& a, const Fe<FP>& b) {

@@ -14,7 +14,9 @@ extern "C" {
 #endif
 /* field ids: 0 pallas_fp, 1 pallas_fq, 2 bn256_fr, 3 bn256_fq
  * op: 0 add, 1 sub, 2 mul, 3 inv(a), 4 from_canonical(a), 5 to_canonical(a), 6 mul by the device's carry-chain
- * algorithm with the carry flag emulated on the host    (Montgomery 32-byte elements) */
+ * algorithm with the carry flag emulated on the host    (Montgomery 32-byte elements);
+ * 7 mul_lazy, 8 add_lazy, 9 sub_lazy, 10 normalise_lazy: the transform's lazily reduced arithmetic (csrc/field.cuh) run on the host
+ * from the same source -- operands are raw 256-bit values in [0, 2p) (b < p for op 7), results of 7-9 come back in [0, 2p) */
 int eagen_selftest_field(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out);
 /* op: 0 complete add (p, q Jacobian), 1 double p, 2 mixed add (q must be z = 1), 3 small multiple k*p.
  * Inputs are Jacobian (96 B); out is affine (64 B), identity = zeros. */

@@ -281,3 +281,34 @@ def test_oracle_synthetic_inputs_are_valid(oracle):
         assert len(set(pts)) == 64
         for x, y in pts:
             assert (y * y - x * x * x - cv.b) % cv.p == 0
+
+
+@pytest.mark.parametrize("field", ["pallas_fp", "pallas_fq", "bn256_fr"])
+def test_lazy_reduction_arithmetic_on_the_host(eagen, field):
+    """the transform's butterflies work on values in [0, 2p) (csrc/field.cuh: mul_lazy / add_lazy / sub_lazy): run the very source on
+    the host (emulated carry flag) and check range and residue class against Python integers, including the corners where a + b
+    carries out of 256 bits (4p > 2^256 for the Pasta moduli) and where a - b borrows"""
+    fid = {"pallas_fp": 0, "pallas_fq": 1, "bn256_fr": 2}[field]
+    p = {"pallas_fp": pyref.Curve("pallas").p, "pallas_fq": pyref.Curve("pallas").q, "bn256_fr": pyref.Curve("grumpkin").p}[field]
+    R = 1 << 256
+    rinv = pow(R, -1, p)
+
+    def words(v):
+        return np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+    def val(w):
+        return sum(int(w[i]) << (64 * i) for i in range(4))
+    rng = pyref.SplitMix64(2026)
+    corner = [0, 1, p - 1, p, p + 1, 2 * p - 1, 2 * p - 2, (2 * p) >> 1, R - 2 * p if R - 2 * p < 2 * p else p]
+    vals = corner + [rng.next_bits(4) % (2 * p) for _ in range(40)]
+    for i, a in enumerate(vals):
+        for b in (vals[(i * 7 + 3) % len(vals)], vals[(i * 5 + 1) % len(vals)], 2 * p - 1, 0):
+            s = val(eagen.selftest_field(fid, 8, words(a), words(b)))
+            assert s < 2 * p and (s - a - b) % p == 0, (field, "add", a, b)
+            d = val(eagen.selftest_field(fid, 9, words(a), words(b)))
+            assert d < 2 * p and (d - a + b) % p == 0, (field, "sub", a, b)
+            w = b % p                                                   # twiddles are canonical
+            m = val(eagen.selftest_field(fid, 7, words(a), words(w)))
+            assert m < 2 * p and (m - a * w * rinv) % p == 0, (field, "mul", a, w)
+            n = val(eagen.selftest_field(fid, 10, words(m)))
+            assert n == a * w * rinv % p, (field, "normalise", a, w)
