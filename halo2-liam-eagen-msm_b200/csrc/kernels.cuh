@@ -4,10 +4,14 @@
 //   K1  k_negbase            negbase_decompose + pad + reverse     src/negbase_utils.rs:20-36, src/argument_witness_calc.rs:93-101
 //   K2  k_multiples_*        precompute_multiplicities (affine)    src/argument_witness_calc.rs:43-51,103
 //   K3  k_digit_sums, k_reduce_partials   the carry += mult[j][digit] loop   src/argument_witness_calc.rs:120-125
-//   K4  k_carry_chain        carry = (-carry)*base + S_i           src/argument_witness_calc.rs:105-127
+//   K4  k_sum_parts, k_carry_chain   carry = (-carry)*base + S_i   src/argument_witness_calc.rs:105-127
+//                            (k_sum_parts folds the ranks' partial sums of a multi-GPU call per position first)
 //   K5  k_pair_den/finish, k_leaf_lines, k_merge_desc   from_pair / from_point / linefunc / output points
 //                                                                    src/regular_functions_utils.rs:285-331,335
+//                            (the whole point pyramid and the inverse denominators run on the engine's side stream)
 //   K6  k_ntt_pass           Polynomial::mul_fft -> best_fft        src/regular_functions_utils.rs:102-129
+//                            (both polynomial families of a level per launch, lazily reduced butterflies, absent tiles skipped;
+//                             k_gen_twiddles / k_gen_points / k_gen_twist_all build the per-context tables)
 //   K7  k_den, k_pointwise, k_fixup   RegularFunction::mul, Propagation::merge, kate_div   :266-273,333-360,45-47
 //   K9  k_binv_*             z.invert() (batched, Montgomery trick) :351-352
 //   K10 k_find_top, k_lead, k_scale   trim + monic canonical form    SURVEY.md section 8c
